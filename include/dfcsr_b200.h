@@ -1,0 +1,186 @@
+/*
+ * dfcsr_b200.h — C ABI of libdfcsr_b200.so: the B200 (sm_100a) implementation of pyDFCSR's
+ * per-step CSR-wake hot path.
+ *
+ * The reference (slaclab/pyDFCSR) has no FFI: the path is reached through Python method calls
+ * (SURVEY.md §8(b)).  Each entry point below replaces the arithmetic behind one of those calls
+ * and cites it (paths relative to /root/reference/pyDFCSR_2D/).  The Python shim in
+ * pydfcsr_b200/ keeps the reference's method names and binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, PODs.  No torch / C++ types cross the boundary.
+ *   - every pointer named d_* is a DEVICE pointer on the current CUDA device; h_* is host memory.
+ *     The caller owns all memory (any allocator); the library allocates nothing persistent.
+ *   - every function returns 0 on success or a negative dfcsr_status; dfcsr_last_error() returns
+ *     a thread-local message.  No exception crosses the boundary.
+ *   - work is enqueued on the caller's stream (void* = cudaStream_t, NULL = default stream) and
+ *     the call returns without synchronising unless stated.
+ *   - all floating-point data are IEEE fp64 ("double"), C order.
+ *
+ * Device layouts
+ *   - "field stack" (SoA): 5 separate (X,Z) arrays, order = dfcsr_field.
+ *   - "voxel slice" (AoS-6): (X,Z,6) doubles = {density, density_x, density_z, vx, vx_x, 0};
+ *     48-byte voxels so that one voxel is three 16-byte vector loads and the two z-neighbours of a
+ *     trilinear cell are 96 contiguous bytes.
+ *   - "history ring": cap voxel slices, slice k of the window lives in slot (head + k) % cap.
+ *   - "lattice table": (ns,6) doubles = {X0, Y0, n_x, n_y, tau_x, tau_y} per sample.
+ */
+#ifndef DFCSR_B200_H
+#define DFCSR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFCSR_ABI_VERSION 1
+#define DFCSR_VOXEL_DOUBLES 6
+#define DFCSR_LATTICE_DOUBLES 6
+#define DFCSR_STATS_DOUBLES 16
+#define DFCSR_DF_SCALARS 8
+#define DFCSR_MAX_ELEMENTS 256
+
+typedef enum dfcsr_status {
+    DFCSR_OK = 0,
+    DFCSR_ERR_INVALID = -1,   /* bad argument                                  */
+    DFCSR_ERR_CUDA = -2,      /* CUDA runtime error (message has the string)   */
+    DFCSR_ERR_UNSUPPORTED = -3, /* size outside what the kernels support        */
+    DFCSR_ERR_WORKSPACE = -4  /* workspace too small                           */
+} dfcsr_status;
+
+typedef enum dfcsr_field {
+    DFCSR_DENSITY = 0, DFCSR_DENSITY_X = 1, DFCSR_DENSITY_Z = 2, DFCSR_VX = 3, DFCSR_VX_X = 4
+} dfcsr_field;
+
+/* indices into the DFCSR_STATS_DOUBLES block written by dfcsr_beam_stats */
+typedef enum dfcsr_stat {
+    DFCSR_S_MEAN_X = 0, DFCSR_S_MEAN_Z = 1, DFCSR_S_SIGMA_X = 2, DFCSR_S_SIGMA_Z = 3,
+    DFCSR_S_SLOPE = 4, DFCSR_S_INTERCEPT = 5,      /* polyfit(z, x, 1)            */
+    DFCSR_S_MEAN_XT = 6, DFCSR_S_SIGMA_XT = 7,     /* x - polyval(slope, z)       */
+    DFCSR_S_SLICE_SIGMA_X = 8, DFCSR_S_SLICE_COUNT = 9, /* |z| < 0.1 sigma_z slice */
+    DFCSR_S_MEAN_PZ = 10, DFCSR_S_SIGMA_PZ = 11, DFCSR_S_N = 12
+} dfcsr_stat;
+
+/* uniform grid described the way numpy.linspace builds it: node i = i*step + start, last = stop */
+typedef struct dfcsr_axis {
+    double start;
+    double stop;
+    int32_t n;
+    int32_t _pad;
+} dfcsr_axis;
+
+/* device-resident (t', x, z) history published by DF_tracker.build_interpolant (deposit.py:395-426) */
+typedef struct dfcsr_history {
+    const double* d_ring;      /* cap voxel slices                                   */
+    int64_t slice_doubles;     /* X * Z * DFCSR_VOXEL_DOUBLES                        */
+    int32_t cap;               /* slots in the ring                                  */
+    int32_t head;              /* slot of the oldest slice in the window             */
+    int32_t T, X, Z;           /* window depth and slice shape                       */
+    int32_t _pad;
+    double min_t, min_x, min_z;      /* deposit.py:416-418 (min_x / min_y / min_z there) */
+    double delta_t, delta_x, delta_z;/* deposit.py:419-421                               */
+} dfcsr_history;
+
+/* reference-orbit tables consumed by the integrand (lattice.py:136-143, CSR.py:619-656) */
+typedef struct dfcsr_lattice {
+    const double* d_table;     /* (ns, 6) lattice table                              */
+    int32_t ns;
+    int32_t n_elements;        /* <= DFCSR_MAX_ELEMENTS                              */
+    double min_s, delta_s;
+    const double* d_rho;       /* (n_elements) curvature per element                 */
+    const double* d_distance;  /* (n_elements) cumulative end position per element   */
+} dfcsr_lattice;
+
+/* scalars read by get_CSR_wake (CSR.py:456-467, 539; CSR.py:80) */
+typedef struct dfcsr_wake_params {
+    double t;                  /* beam.position                                      */
+    double sigma_x, sigma_z;   /* beam._sigma_x / _sigma_z                           */
+    double slope0;             /* beam._slope[0]                                     */
+    double mean_x;             /* beam._mean_x                                       */
+    double formation_window;   /* n_formation_length * formation_length              */
+    double csr_scaling;        /* 8.98755e3 * charge                                 */
+    int32_t nx, nz;            /* integration_params.xbins / zbins                   */
+} dfcsr_wake_params;
+
+int dfcsr_abi_version(void);
+const char* dfcsr_last_error(void);
+
+/* ---- A14 beam scalars (beams.py:88-98,137-156,201-215; deposit.py:147-159) --------------------
+ * Three reduction passes over (x, z[, pz]); results land in d_stats[DFCSR_STATS_DOUBLES].
+ * d_workspace needs dfcsr_beam_stats_workspace() bytes.  d_pz may be NULL. */
+int64_t dfcsr_beam_stats_workspace(void);
+int dfcsr_beam_stats(const double* d_x, const double* d_z, const double* d_pz, int64_t n,
+                     double* d_stats, void* d_workspace, void* stream);
+
+/* ---- A1 / K1 particle deposition (deposit.py:42-87, called at deposit.py:172,178) --------------
+ * One pass deposits both weights (w = 1 and w = px) with CIC on an (nx, nz) grid whose bin spacing
+ * is (end - start) / n.  d_count / d_vxsum (nx*nz doubles each) are zeroed by the call.
+ * mode 0 = automatic, 1 = block-private shared-memory tiles, 2 = direct L2 reductions. */
+int dfcsr_deposit_cic(const double* d_x, const double* d_z, const double* d_px, int64_t n,
+                      int32_t nx, double x_start, double x_end,
+                      int32_t nz, double z_start, double z_end,
+                      double* d_count, double* d_vxsum, int32_t mode, void* stream);
+
+/* NGP counts (no reference counterpart): i = floor((q - start)/spacing + 0.5),
+ * +1 iff both indices are in range; int64 counts, bit-exact for any summation order. */
+int dfcsr_deposit_ngp(const double* d_x, const double* d_z, int64_t n,
+                      int32_t nx, double x_start, double x_end,
+                      int32_t nz, double z_start, double z_end,
+                      int64_t* d_count, void* stream);
+
+/* ---- A2-A4 / K2 density functions (deposit.py:183-235) -----------------------------------------
+ * count / vxsum -> the five smoothed fields.  Savitzky-Golay operators for (window, order) are
+ * host-computed: h_taps[window], h_edge_lo[half*window], h_edge_hi[half*window] (half = window/2).
+ * d_fields: field stack (5, nx, nz).  d_scalars[DFCSR_DF_SCALARS] receives
+ *   [0] max(count)  [1] threshold  [2] trapz normalisation  [3] max(density)
+ *   [4] mean(vx_x) after the mask fill (= fill value used by the re-gridding, deposit.py:332)
+ *   [5] masked mean  [6] number of cells above the second threshold.
+ * d_workspace needs dfcsr_make_df_workspace(nx, nz) bytes. */
+int64_t dfcsr_make_df_workspace(int32_t nx, int32_t nz);
+int dfcsr_make_df(const double* d_count, const double* d_vxsum, dfcsr_axis x_axis, dfcsr_axis z_axis,
+                  int32_t window, const double* h_taps, const double* h_edge_lo, const double* h_edge_hi,
+                  double velocity_threshold, double* d_fields, double* d_scalars,
+                  void* d_workspace, void* stream);
+
+/* ---- A7 / K3 bilinear re-gridding into a history slot (deposit.py:296-309,328-332,379-390) -----
+ * Samples the five fields of one raw density-function record (field stack on src axes) on the
+ * history grid and writes one voxel slice.  Out-of-source points get 0, or the fill value for vx_x
+ * (np.mean(vx_x), deposit.py:332,384): *d_fill_vx_x when that device pointer is non-NULL (e.g.
+ * scalars[4] of dfcsr_make_df, so the host never has to read it back), else fill_vx_x. */
+int dfcsr_history_regrid(const double* d_fields, dfcsr_axis src_x, dfcsr_axis src_z,
+                         dfcsr_axis dst_x, dfcsr_axis dst_z, double fill_vx_x, const double* d_fill_vx_x,
+                         double* d_slice, void* stream);
+
+/* field stack (5, X, Z) <-> voxel slice (X, Z, 6): import/export of oracle histories in tests */
+int dfcsr_history_pack(const double* d_fields, int32_t X, int32_t Z, double* d_slice, void* stream);
+int dfcsr_history_unpack(const double* d_slice, int32_t X, int32_t Z, double* d_fields, void* stream);
+
+/* ---- A10-A12 / K4 wake on the observation mesh (CSR.py:397-451, 454-602, 605-782) --------------
+ * For k in [0, count): s = t + d_zmesh[first + k], x = d_xmesh[first + k];
+ * d_dE[k], d_kick[k] = get_CSR_wake(s, x).  first/count implement the reference's MPI block split
+ * (CSR.py:121-125, 434-445).  d_counters (may be NULL): [0] += in-grid integrand samples,
+ * [1] += evaluated samples (device-side accounting for the roofline figure). */
+int dfcsr_wake_mesh(const dfcsr_history* hist, const dfcsr_lattice* lat, const dfcsr_wake_params* wp,
+                    const double* d_xmesh, const double* d_zmesh, int64_t first, int64_t count,
+                    double* d_dE, double* d_kick, unsigned long long* d_counters, void* stream);
+
+/* get_CSR_wake(s, x, debug=True) (CSR.py:571-572, 599-600): integrands of one point.
+ * d_iz / d_ix receive the regions back to back, each (n_x, n_s) row-major like the reference's
+ * CSR_integrand_z/x arrays; h_regions[4][6] = {x_lo, x_hi, n_x, s_lo, s_hi, n_s}.  Synchronises. */
+int dfcsr_wake_point_debug(const dfcsr_history* hist, const dfcsr_lattice* lat, const dfcsr_wake_params* wp,
+                           double s, double x, double* d_iz, double* d_ix, int64_t capacity,
+                           double* h_regions, int32_t* h_n_regions, void* stream);
+
+/* ---- A13 / K5 kick application (beams.py:108-131) ----------------------------------------------
+ * pz += bilinear(step*dE*1e6/E0)(x_T, z); px += bilinear(step*kick*1e6/E0)(x_T, z) if transverse_on,
+ * with x_T = x - (slope*z + intercept), zero outside the mesh.  In place on d_px / d_pz. */
+int dfcsr_apply_kick(const double* d_x, const double* d_z, double* d_px, double* d_pz, int64_t n,
+                     double slope, double intercept,
+                     const double* d_dE, const double* d_kick, dfcsr_axis x_axis, dfcsr_axis z_axis,
+                     double step_size, double init_energy, int32_t transverse_on, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFCSR_B200_H */

@@ -1,0 +1,105 @@
+"""ctypes binding of libdfcsr_b200.so (include/dfcsr_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing or does not export the ABI
+declared in the header, importing this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdfcsr_b200.so")
+
+VOXEL_DOUBLES = 6
+LATTICE_DOUBLES = 6
+STATS_DOUBLES = 16
+DF_SCALARS = 8
+ABI_VERSION = 1
+
+# indices of dfcsr_stat
+(S_MEAN_X, S_MEAN_Z, S_SIGMA_X, S_SIGMA_Z, S_SLOPE, S_INTERCEPT, S_MEAN_XT, S_SIGMA_XT,
+ S_SLICE_SIGMA_X, S_SLICE_COUNT, S_MEAN_PZ, S_SIGMA_PZ, S_N) = range(13)
+
+
+class Axis(C.Structure):
+    _fields_ = [("start", C.c_double), ("stop", C.c_double), ("n", C.c_int32), ("_pad", C.c_int32)]
+
+    @classmethod
+    def make(cls, start, stop, n):
+        return cls(float(start), float(stop), int(n), 0)
+
+
+class History(C.Structure):
+    _fields_ = [("d_ring", C.c_void_p), ("slice_doubles", C.c_int64), ("cap", C.c_int32), ("head", C.c_int32),
+                ("T", C.c_int32), ("X", C.c_int32), ("Z", C.c_int32), ("_pad", C.c_int32),
+                ("min_t", C.c_double), ("min_x", C.c_double), ("min_z", C.c_double),
+                ("delta_t", C.c_double), ("delta_x", C.c_double), ("delta_z", C.c_double)]
+
+
+class Lattice(C.Structure):
+    _fields_ = [("d_table", C.c_void_p), ("ns", C.c_int32), ("n_elements", C.c_int32),
+                ("min_s", C.c_double), ("delta_s", C.c_double), ("d_rho", C.c_void_p), ("d_distance", C.c_void_p)]
+
+
+class WakeParams(C.Structure):
+    _fields_ = [("t", C.c_double), ("sigma_x", C.c_double), ("sigma_z", C.c_double), ("slope0", C.c_double),
+                ("mean_x", C.c_double), ("formation_window", C.c_double), ("csr_scaling", C.c_double),
+                ("nx", C.c_int32), ("nz", C.c_int32)]
+
+
+_P = C.c_void_p
+_D = C.c_double
+_I = C.c_int32
+_L = C.c_int64
+
+# name -> (restype, argtypes); must list every symbol declared in include/dfcsr_b200.h
+SIGNATURES = {
+    "dfcsr_abi_version": (C.c_int, []),
+    "dfcsr_last_error": (C.c_char_p, []),
+    "dfcsr_beam_stats_workspace": (_L, []),
+    "dfcsr_beam_stats": (C.c_int, [_P, _P, _P, _L, _P, _P, _P]),
+    "dfcsr_deposit_cic": (C.c_int, [_P, _P, _P, _L, _I, _D, _D, _I, _D, _D, _P, _P, _I, _P]),
+    "dfcsr_deposit_ngp": (C.c_int, [_P, _P, _L, _I, _D, _D, _I, _D, _D, _P, _P]),
+    "dfcsr_make_df_workspace": (_L, [_I, _I]),
+    "dfcsr_make_df": (C.c_int, [_P, _P, Axis, Axis, _I, _P, _P, _P, _D, _P, _P, _P, _P]),
+    "dfcsr_history_regrid": (C.c_int, [_P, Axis, Axis, Axis, Axis, _D, _P, _P, _P]),
+    "dfcsr_history_pack": (C.c_int, [_P, _I, _I, _P, _P]),
+    "dfcsr_history_unpack": (C.c_int, [_P, _I, _I, _P, _P]),
+    "dfcsr_wake_mesh": (C.c_int, [C.POINTER(History), C.POINTER(Lattice), C.POINTER(WakeParams),
+                                  _P, _P, _L, _L, _P, _P, _P, _P]),
+    "dfcsr_wake_point_debug": (C.c_int, [C.POINTER(History), C.POINTER(Lattice), C.POINTER(WakeParams),
+                                         _D, _D, _P, _P, _L, _P, _P, _P]),
+    "dfcsr_apply_kick": (C.c_int, [_P, _P, _P, _P, _L, _D, _D, _P, _P, Axis, Axis, _D, _D, _I, _P]),
+}
+
+
+class DfcsrError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m pydfcsr_b200.build` "
+            "(pydfcsr_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise ImportError(f"libdfcsr_b200.so does not export {name}") from e
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dfcsr_abi_version() != ABI_VERSION:
+        raise ImportError("libdfcsr_b200.so ABI version mismatch; rebuild")
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib.dfcsr_last_error().decode("utf-8", "replace")
+        raise DfcsrError(f"{what or 'libdfcsr_b200'} failed ({rc}): {msg}")

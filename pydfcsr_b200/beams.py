@@ -1,0 +1,163 @@
+"""Device-resident ``Beam`` with the reference's public surface (beams.py:12-229): construction from
+the ``input_beam`` YAML block, ``track``, ``apply_wakes``, ``update_status`` and the statistics
+properties read by the hot path (``_sigma_x, _sigma_z, _slope, _mean_x, _mean_z, x_transform``).
+
+Particles are six CUDA float64 tensors (Bmad-X order x, px, y, py, z, pz); they are uploaded once
+and stay in HBM across tracking, deposition and kick application.  All O(Np) statistics come from
+one call of the device reduction kernels per state change (``ops.beam_stats``), not from numpy.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib, ops, synth, tracking
+from ._lib import Axis
+
+MC2 = 0.51099895e6      # electron rest energy [eV] (physical_constants.py)
+
+
+class Beam:
+    def __init__(self, input_beam, device=None):
+        self.check_inputs(input_beam)
+        self.input_beam_config = input_beam
+        self.style = input_beam["style"]
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.style == "from_file":                                  # beams.py:22-35
+            coords = np.loadtxt(input_beam["beamfile"])
+            assert coords.shape[1] == 6, f"Error: input beam must have 6 dimension, but get {coords.shape[1]} instead"
+            coords = coords.T
+            self._charge = input_beam["charge"]
+            self._init_energy = input_beam["energy"]
+        elif self.style == "array":                                    # in-memory (6, Np) array or tensor
+            coords = input_beam["coords"]
+            self._charge = input_beam["charge"]
+            self._init_energy = input_beam["energy"]
+        elif self.style == "synthetic":                                # seeded Gaussian (distgen stand-in)
+            kw = {k: v for k, v in input_beam.items() if k not in ("style", "verbose")}
+            n = kw.pop("n_particle")
+            coords = synth.gaussian_bunch(n, **kw)
+            self._charge = input_beam.get("charge", synth.CHICANE_BEAM["charge"])
+            self._init_energy = input_beam.get("energy", synth.CHICANE_BEAM["energy"])
+        elif self.style == "distgen":                                  # beams.py:38-46
+            try:
+                from distgen import Generator
+            except ImportError as e:
+                raise ImportError("input_beam style 'distgen' needs the distgen package; use style "
+                                  "'from_file', 'array' or 'synthetic' instead") from e
+            gen = Generator(input_beam["distgen_input_file"])
+            gen.run()
+            pg = gen.particles
+            self._charge = pg["charge"]
+            self._init_energy = float(np.mean(pg["energy"]))
+            p0c = self._init_energy
+            coords = np.stack([pg.x, pg.px / p0c, pg.y, pg.py / p0c,
+                               -299792458.0 * pg.beta * (pg.t - np.mean(pg.t)), (pg.p - p0c) / p0c])
+        else:
+            raise ImportError("input_beam style 'ParticleGroup' needs pmd_beamphysics/h5py (not available offline)")
+        if isinstance(coords, torch.Tensor):
+            c = coords.to(self.device, torch.float64)
+        else:
+            c = torch.from_numpy(np.ascontiguousarray(coords, dtype=np.float64)).to(self.device)
+        self.coords = [c[k].contiguous() for k in range(6)]
+        self._init_gamma = self._init_energy / MC2
+        self.position = 0
+        self.step = 0
+        self.update_status()
+
+    def check_inputs(self, input_beam):
+        assert "style" in input_beam, "ERROR: input_beam must have keyword <style>"
+        required = {"from_file": ["style", "beamfile", "charge", "energy"],
+                    "distgen": ["style", "distgen_input_file"],
+                    "ParticleGroup": ["style", "ParticleGroup_h5"],
+                    "array": ["style", "coords", "charge", "energy"],
+                    "synthetic": ["style", "n_particle"]}
+        if input_beam["style"] not in required:
+            raise Exception("input beam parsing Error: invalid input style")
+        self.required_inputs = required[input_beam["style"]]
+        for req in self.required_inputs:
+            assert req in input_beam, f"Required input parameter {req} to Beam.__init__(**kwargs) was not found."
+        if input_beam["style"] != "synthetic":
+            allowed = self.required_inputs + ["verbose"]
+            for key in input_beam:
+                assert key in allowed, f"Incorrect param given to Beam.__init__(**kwargs): {key}\nAllowed params: {allowed}"
+
+    # ------------------------------------------------------------------------------- state
+    def update_status(self):
+        """One pass of the device reductions replaces np.std/np.mean/np.polyfit (beams.py:88-98)."""
+        st = ops.beam_stats(self.x, self.z, self.pz)
+        self.stats = st
+        self._sigma_x = float(st[_lib.S_SIGMA_X])
+        self._sigma_z = float(st[_lib.S_SIGMA_Z])
+        self._slope = np.array([st[_lib.S_SLOPE], st[_lib.S_INTERCEPT]])
+        self._mean_x = float(st[_lib.S_MEAN_X])
+        self._mean_z = float(st[_lib.S_MEAN_Z])
+
+    def track(self, element, step_size, update_step=True):
+        """beams.py:101-106.  `element` is a tracking.* element (stand-in for bmadx.track_element)."""
+        self.coords = [c.contiguous() for c in tracking.track_linear(tuple(self.coords), element)]
+        self.position += step_size
+        if update_step:
+            self.step += 1
+        self.update_status()
+
+    def apply_wakes(self, dE_dct, x_kick, xrange, zrange, step_size, transverse_on):
+        """beams.py:108-131 on the device, in place."""
+        dE = dE_dct if isinstance(dE_dct, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(dE_dct)).to(self.device)
+        kick = x_kick if isinstance(x_kick, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x_kick)).to(self.device)
+        xa = Axis.make(xrange[0], xrange[-1], len(xrange))
+        za = Axis.make(zrange[0], zrange[-1], len(zrange))
+        ops.apply_kick(self.x, self.z, self.coords[1], self.coords[5], self._slope[0], self._slope[1],
+                       dE.contiguous(), kick.contiguous(), xa, za, step_size, self.init_energy, transverse_on)
+        self.update_status()
+
+    # ------------------------------------------------------------------------------- properties
+    x = property(lambda self: self.coords[0])
+    px = property(lambda self: self.coords[1])
+    y = property(lambda self: self.coords[2])
+    py = property(lambda self: self.coords[3])
+    z = property(lambda self: self.coords[4])
+    pz = property(lambda self: self.coords[5])
+    mean_x = property(lambda self: self._mean_x)
+    mean_z = property(lambda self: self._mean_z)
+    sigma_x = property(lambda self: self._sigma_x)
+    sigma_z = property(lambda self: self._sigma_z)
+    slope = property(lambda self: self._slope)
+    init_energy = property(lambda self: self._init_energy)
+    init_gamma = property(lambda self: self._init_gamma)
+    charge = property(lambda self: self._charge)
+    mean_y = property(lambda self: float(self.y.mean()))
+    mean_energy = property(lambda self: (float(self.stats[_lib.S_MEAN_PZ]) + 1) * self._init_energy)
+    sigma_energy = property(lambda self: float(self.stats[_lib.S_SIGMA_PZ]) * self._init_energy)
+    sigma_x_transform = property(lambda self: float(self.stats[_lib.S_SIGMA_XT]))
+    mean_x_transform = property(lambda self: float(self.stats[_lib.S_MEAN_XT]))
+
+    @property
+    def energy(self):
+        return (self.pz + 1) * self._init_energy
+
+    @property
+    def gamma(self):
+        return self.energy / MC2
+
+    @property
+    def x_transform(self):
+        """x with the x-z chirp removed (beams.py:206-211); a device tensor."""
+        return self.x - (self._slope[0] * self.z + self._slope[1])
+
+    @property
+    def twiss(self):
+        """Twiss/dispersion from the 3x3 covariances (twiss.py:2-71), computed with torch on device."""
+        out = {}
+        for plane, (q, p) in (("x", (self.x, self.px)), ("y", (self.y, self.py))):
+            cov = torch.cov(torch.stack([q, p, self.pz])).cpu().numpy()
+            d2, xd, pd = cov[2, 2], cov[0, 2], cov[1, 2]
+            eb, eg, ea = cov[0, 0] - xd ** 2 / d2, cov[1, 1] - pd ** 2 / d2, -cov[0, 1] + xd * pd / d2
+            emit = np.sqrt(eb * eg - ea ** 2)
+            vals = dict(alpha=ea / emit, beta=eb / emit, gamma=eg / emit, emit=emit, eta=xd / d2, etap=pd / d2,
+                        norm_emit=emit * self._init_energy / MC2)
+            out.update({f"{k}_{plane}": v for k, v in vals.items()})
+        return out
+
+    def to_host(self) -> np.ndarray:
+        return torch.stack(self.coords).cpu().numpy()

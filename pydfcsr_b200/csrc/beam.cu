@@ -1,0 +1,232 @@
+// beam.cu — A14 beam scalars and K5 kick application.
+//
+// dfcsr_beam_stats replaces the O(Np) numpy reductions the reference performs on the host every
+// step: np.std / np.mean / np.polyfit(z, x, 1) in Beam.update_status (beams.py:88-98,137-156,
+// 201-215), the slice test of DF_tracker.get_DF (deposit.py:147-159) and the statistics of
+// x_transform used by get_CSR_mesh (CSR.py:368-374).  Three two-level deterministic reductions
+// (fixed grid, fixed summation order -> bitwise reproducible); only 16 doubles go back to the host.
+//
+// dfcsr_apply_kick replaces Beam.apply_wakes (beams.py:108-131): bilinear samples
+// (RegularGridInterpolator, fill 0) of the two wake grids at (x - polyval(slope, z), z).
+// Bound: HBM, 48 B / particle (read x, z, px, pz; write px, pz).
+#include "common.cuh"
+
+namespace dfcsr {
+
+constexpr int kStatThreads = 256;
+constexpr int kStatBlocks = 148 * 4;
+constexpr int kStatVals = 6;
+
+struct StatWorkspace {
+    double partial[3][kStatBlocks][kStatVals];
+    unsigned int ticket[4];
+};
+
+template <int NV>
+__device__ __forceinline__ bool block_reduce_publish(double (&v)[NV], double (*partial)[kStatVals],
+                                                     unsigned int* ticket, double (&total)[NV]) {
+    __shared__ double sm[kStatThreads / 32][kStatVals];
+    __shared__ bool last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+    if (lane == 0)
+        for (int k = 0; k < NV; ++k) sm[warp][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < NV; ++k) {
+            double s = 0.0;
+            for (int w = 0; w < kStatThreads / 32; ++w) s += sm[w][k];
+            partial[blockIdx.x][k] = s;
+        }
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return false;
+    __threadfence();
+    // the last block to arrive sums the partials in block order (deterministic)
+    for (int k = 0; k < NV; ++k) {
+        double s = 0.0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += kStatThreads) s += ((volatile double*)&partial[b][k])[0];
+        v[k] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+    if (lane == 0)
+        for (int k = 0; k < NV; ++k) sm[warp][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < NV; ++k) {
+            double s = 0.0;
+            for (int w = 0; w < kStatThreads / 32; ++w) s += sm[w][k];
+            total[k] = s;
+        }
+        *ticket = 0u;
+    }
+    return threadIdx.x == 0;
+}
+
+__global__ void __launch_bounds__(kStatThreads)
+stats_pass1(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ pz,
+            long long n, double* __restrict__ stats, StatWorkspace* ws) {
+    double v[3] = {0.0, 0.0, 0.0};
+    for (long long i = (long long)blockIdx.x * kStatThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kStatThreads) {
+        v[0] += x[i];
+        v[1] += z[i];
+        if (pz) v[2] += pz[i];
+    }
+    double tot[3];
+    if (block_reduce_publish<3>(v, ws->partial[0], &ws->ticket[0], tot)) {
+        stats[DFCSR_S_MEAN_X] = tot[0] / (double)n;
+        stats[DFCSR_S_MEAN_Z] = tot[1] / (double)n;
+        stats[DFCSR_S_MEAN_PZ] = tot[2] / (double)n;
+        stats[DFCSR_S_N] = (double)n;
+    }
+}
+
+__global__ void __launch_bounds__(kStatThreads)
+stats_pass2(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ pz,
+            long long n, double* __restrict__ stats, StatWorkspace* ws) {
+    const double mx = stats[DFCSR_S_MEAN_X], mz = stats[DFCSR_S_MEAN_Z], mp = stats[DFCSR_S_MEAN_PZ];
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long long i = (long long)blockIdx.x * kStatThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kStatThreads) {
+        double dx = x[i] - mx, dz = z[i] - mz;
+        v[0] = fma(dx, dx, v[0]);
+        v[1] = fma(dz, dz, v[1]);
+        v[2] = fma(dx, dz, v[2]);
+        if (pz) {
+            double dp = pz[i] - mp;
+            v[3] = fma(dp, dp, v[3]);
+        }
+    }
+    double tot[4];
+    if (block_reduce_publish<4>(v, ws->partial[1], &ws->ticket[1], tot)) {
+        stats[DFCSR_S_SIGMA_X] = sqrt(tot[0] / (double)n);   // np.std: population (ddof = 0)
+        stats[DFCSR_S_SIGMA_Z] = sqrt(tot[1] / (double)n);
+        double slope = tot[2] / tot[1];                       // least-squares line x = slope z + b
+        stats[DFCSR_S_SLOPE] = slope;
+        stats[DFCSR_S_INTERCEPT] = mx - slope * mz;
+        stats[DFCSR_S_SIGMA_PZ] = sqrt(tot[3] / (double)n);
+    }
+}
+
+__global__ void __launch_bounds__(kStatThreads)
+stats_pass3(const double* __restrict__ x, const double* __restrict__ z, long long n,
+            double* __restrict__ stats, StatWorkspace* ws) {
+    const double mx = stats[DFCSR_S_MEAN_X], mz = stats[DFCSR_S_MEAN_Z];
+    const double slope = stats[DFCSR_S_SLOPE];
+    const double cut = 0.1 * stats[DFCSR_S_SIGMA_Z];
+    double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (long long i = (long long)blockIdx.x * kStatThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kStatThreads) {
+        double zi = z[i];
+        double dx = x[i] - mx;
+        double e = dx - slope * (zi - mz);   // x_transform up to the (rounding-level) constant term
+        v[0] += e;
+        v[1] = fma(e, e, v[1]);
+        if (fabs(zi) < cut) {                // deposit.py:157: |z|, not |z - mean z|
+            v[2] += dx;
+            v[3] = fma(dx, dx, v[3]);
+            v[4] += 1.0;
+        }
+    }
+    double tot[5];
+    if (block_reduce_publish<5>(v, ws->partial[2], &ws->ticket[2], tot)) {
+        double me = tot[0] / (double)n;
+        stats[DFCSR_S_MEAN_XT] = me;
+        stats[DFCSR_S_SIGMA_XT] = sqrt(fmax(tot[1] / (double)n - me * me, 0.0));
+        double c = tot[4];
+        double ms = tot[2] / c;
+        stats[DFCSR_S_SLICE_SIGMA_X] = sqrt(fmax(tot[3] / c - ms * ms, 0.0));
+        stats[DFCSR_S_SLICE_COUNT] = c;
+    }
+}
+
+// ---- K5 ---------------------------------------------------------------------------------------
+struct Cell1 {
+    int i;
+    double y;
+    bool outside;
+};
+
+// RegularGridInterpolator's per-axis search on linspace nodes (see history.cu::locate)
+__device__ __forceinline__ Cell1 locate1(const Axis& g, double q) {
+    Cell1 c;
+    c.outside = (q < g.start) || (q > g.stop) || !(q == q);
+    int i = 0;
+    if (g.step > 0.0 && !c.outside) {
+        double guess = floor((q - g.start) / g.step);
+        i = (guess < 0.0) ? 0 : ((guess > (double)(g.n - 2)) ? g.n - 2 : (int)guess);
+        while (i > 0 && axis_node(g, i) > q) --i;
+        while (i < g.n - 2 && axis_node(g, i + 1) <= q) ++i;
+    }
+    c.i = i;
+    double a = axis_node(g, i), b = axis_node(g, i + 1);
+    c.y = (q - a) / (b - a);
+    return c;
+}
+
+__global__ void __launch_bounds__(256)
+apply_kick_kernel(const double* __restrict__ x, const double* __restrict__ z, double* __restrict__ px,
+                  double* __restrict__ pz, long long n, double slope, double intercept,
+                  const double* __restrict__ dE, const double* __restrict__ kick, Axis ax, Axis az,
+                  double factor, int transverse_on) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        const double zp = z[p];
+        const double xt = __dsub_rn(x[p], __dadd_rn(__dmul_rn(slope, zp), intercept));   // x - polyval(slope, z)
+        Cell1 cx = locate1(ax, xt), cz = locate1(az, zp);
+        if (cx.outside || cz.outside) continue;   // fill_value = 0: nothing to add
+        const double wx0 = 1.0 - cx.y, wz0 = 1.0 - cz.y;
+        const double w00 = wx0 * wz0, w01 = wx0 * cz.y, w10 = cx.y * wz0, w11 = cx.y * cz.y;
+        const size_t o = (size_t)cx.i * az.n + cz.i;
+        double e = __ldg(dE + o) * w00 + __ldg(dE + o + 1) * w01 + __ldg(dE + o + az.n) * w10 + __ldg(dE + o + az.n + 1) * w11;
+        pz[p] += factor * e;
+        if (transverse_on) {
+            double k = __ldg(kick + o) * w00 + __ldg(kick + o + 1) * w01 + __ldg(kick + o + az.n) * w10 + __ldg(kick + o + az.n + 1) * w11;
+            px[p] += factor * k;
+        }
+    }
+}
+
+}  // namespace dfcsr
+
+using namespace dfcsr;
+
+extern "C" int64_t dfcsr_beam_stats_workspace(void) { return (int64_t)sizeof(StatWorkspace); }
+
+extern "C" int dfcsr_beam_stats(const double* d_x, const double* d_z, const double* d_pz, int64_t n,
+                                double* d_stats, void* d_workspace, void* stream) {
+    DFCSR_REQUIRE(d_x && d_z && d_stats && d_workspace, "null pointer");
+    DFCSR_REQUIRE(n >= 2, "need at least two particles");
+    cudaStream_t st = as_stream(stream);
+    StatWorkspace* ws = reinterpret_cast<StatWorkspace*>(d_workspace);
+    DFCSR_CUDA_OK(cudaMemsetAsync(ws->ticket, 0, sizeof(ws->ticket), st));
+    DFCSR_CUDA_OK(cudaMemsetAsync(d_stats, 0, sizeof(double) * DFCSR_STATS_DOUBLES, st));
+    long long want = (n + kStatThreads - 1) / kStatThreads;
+    unsigned blocks = (unsigned)(want < kStatBlocks ? want : kStatBlocks);
+    stats_pass1<<<blocks, kStatThreads, 0, st>>>(d_x, d_z, d_pz, n, d_stats, ws);
+    stats_pass2<<<blocks, kStatThreads, 0, st>>>(d_x, d_z, d_pz, n, d_stats, ws);
+    stats_pass3<<<blocks, kStatThreads, 0, st>>>(d_x, d_z, n, d_stats, ws);
+    DFCSR_CUDA_OK(cudaGetLastError());
+    return DFCSR_OK;
+}
+
+extern "C" int dfcsr_apply_kick(const double* d_x, const double* d_z, double* d_px, double* d_pz, int64_t n,
+                                double slope, double intercept, const double* d_dE, const double* d_kick,
+                                dfcsr_axis x_axis, dfcsr_axis z_axis, double step_size, double init_energy,
+                                int32_t transverse_on, void* stream) {
+    DFCSR_REQUIRE(n >= 0, "negative particle count");
+    DFCSR_REQUIRE(d_dE && d_kick && (n == 0 || (d_x && d_z && d_px && d_pz)), "null pointer");
+    DFCSR_REQUIRE(x_axis.n >= 2 && z_axis.n >= 2, "wake mesh needs at least 2 nodes per axis");
+    if (n == 0) return DFCSR_OK;
+    Axis ax = make_axis(x_axis.start, x_axis.stop, x_axis.n), az = make_axis(z_axis.start, z_axis.stop, z_axis.n);
+    const double factor = step_size * 1e6 / init_energy;   // beams.py:110,117
+    long long want = (n + 255) / 256;
+    unsigned blocks = (unsigned)(want < 148LL * 8 ? want : 148LL * 8);
+    apply_kick_kernel<<<blocks, 256, 0, as_stream(stream)>>>(d_x, d_z, d_px, d_pz, n, slope, intercept, d_dE,
+                                                           d_kick, ax, az, factor, transverse_on);
+    DFCSR_CUDA_OK(cudaGetLastError());
+    return DFCSR_OK;
+}

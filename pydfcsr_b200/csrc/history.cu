@@ -1,0 +1,157 @@
+// history.cu — K3: bilinear re-gridding of one raw density-function record into a voxel slice of the
+// device-resident history ring, plus SoA<->AoS converters used to import/export oracle histories.
+//
+// Replaces DF_tracker.DF_interp (deposit.py:296-309), i.e. scipy RegularGridInterpolator(method=
+// 'linear', bounds_error=False, fill_value=f) evaluated on meshgrid(x_grid_interp, z_grid_interp),
+// called five times per step (deposit.py:328-332) or 5*T times on a rebuild (deposit.py:379-390),
+// and the np.array(deque) re-stack of build_interpolant (deposit.py:422-426): the slice is written
+// in place into its ring slot, so nothing is re-stacked or copied per step.
+//
+// scipy semantics restated (scipy/interpolate/_rgi.py:446-477,635-642):
+//   per axis  i = clip(searchsorted(g, q, 'right') - 1, 0, n-2),  y = (q - g[i]) / (g[i+1] - g[i])
+//   value     F[i,j](1-yx)(1-yz) + F[i,j+1](1-yx)yz + F[i+1,j]yx(1-yz) + F[i+1,j+1]yx yz
+//   fill      where q < g[0] or q > g[-1] on either axis.
+// Products/sums use explicit round-to-nearest intrinsics (no FMA contraction) so that, given
+// identical source fields, the slice is bit-identical to scipy's.
+//
+// Bound: HBM write of X*Z*48 B per slice (the source, <= 300x300x5 doubles, stays in L2).
+#include "common.cuh"
+
+namespace dfcsr {
+
+constexpr int kRegridCols = 128;   // threads per block = columns (z) per tile
+constexpr int kRegridRows = 16;    // rows (x) per tile
+
+struct AxisCell {
+    int i;
+    double y;
+    int outside;
+};
+
+// searchsorted(g, q, 'right') - 1 on linspace nodes: arithmetic guess, then exact fix-up against the
+// bit-exact node values.
+__device__ inline AxisCell locate(const Axis& g, double q) {
+    AxisCell c;
+    const int n = g.n;
+    double g0 = g.start, gl = g.stop;
+    c.outside = (q < g0) || (q > gl) || !(q == q);
+    int i = 0;
+    if (g.step > 0.0 && q == q) {
+        double guess = floor((q - g0) / g.step);
+        i = (guess < 0.0) ? 0 : ((guess > (double)(n - 2)) ? n - 2 : (int)guess);
+        while (i > 0 && axis_node(g, i) > q) --i;              // need g[i] <= q
+        while (i < n - 2 && axis_node(g, i + 1) <= q) ++i;     // and q < g[i+1]
+    }
+    c.i = i;
+    double a = axis_node(g, i), b = axis_node(g, i + 1);
+    c.y = __ddiv_rn(__dsub_rn(q, a), __dsub_rn(b, a));
+    return c;
+}
+
+__global__ void __launch_bounds__(kRegridCols)
+regrid_kernel(const double* __restrict__ src, Axis sx, Axis sz, Axis dx, Axis dz, double fill_vx_x,
+              const double* __restrict__ fill_ptr, double* __restrict__ slice) {
+    __shared__ AxisCell rows[kRegridRows];
+    if (fill_ptr) fill_vx_x = __ldg(fill_ptr);
+    const int col = blockIdx.x * kRegridCols + threadIdx.x;
+    const int row0 = blockIdx.y * kRegridRows;
+    if (threadIdx.x < kRegridRows && row0 + threadIdx.x < dx.n)
+        rows[threadIdx.x] = locate(sx, axis_node(dx, row0 + threadIdx.x));
+    AxisCell cz;
+    cz.i = 0; cz.y = 0.0; cz.outside = 1;
+    if (col < dz.n) cz = locate(sz, axis_node(dz, col));
+    __syncthreads();
+    if (col >= dz.n) return;
+    const size_t plane = (size_t)sx.n * sz.n;
+    const double wz1 = cz.y, wz0 = __dsub_rn(1.0, cz.y);
+    const int rmax = min(kRegridRows, dx.n - row0);
+    for (int r = 0; r < rmax; ++r) {
+        const AxisCell cx = rows[r];
+        double out[DFCSR_VOXEL_DOUBLES];
+        if (cx.outside || cz.outside) {
+            out[0] = out[1] = out[2] = out[3] = 0.0;
+            out[4] = fill_vx_x;
+        } else {
+            const double wx1 = cx.y, wx0 = __dsub_rn(1.0, cx.y);
+            const size_t o = (size_t)cx.i * sz.n + cz.i;
+#pragma unroll
+            for (int f = 0; f < 5; ++f) {
+                // scipy's evaluate_linear_2d order: ((F * wx) * wz), corners accumulated in sequence
+                const double* p = src + f * plane + o;
+                double v = __dmul_rn(__dmul_rn(__ldg(p), wx0), wz0);
+                v = __dadd_rn(v, __dmul_rn(__dmul_rn(__ldg(p + 1), wx0), wz1));
+                v = __dadd_rn(v, __dmul_rn(__dmul_rn(__ldg(p + sz.n), wx1), wz0));
+                v = __dadd_rn(v, __dmul_rn(__dmul_rn(__ldg(p + sz.n + 1), wx1), wz1));
+                out[f] = v;
+            }
+        }
+        out[5] = 0.0;
+        double2* dst = reinterpret_cast<double2*>(slice + ((size_t)(row0 + r) * dz.n + col) * DFCSR_VOXEL_DOUBLES);
+        dst[0] = make_double2(out[0], out[1]);
+        dst[1] = make_double2(out[2], out[3]);
+        dst[2] = make_double2(out[4], out[5]);
+    }
+}
+
+__global__ void pack_kernel(const double* __restrict__ fields, long long cells, double* __restrict__ slice) {
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < cells;
+         c += (long long)gridDim.x * blockDim.x) {
+        double2* dst = reinterpret_cast<double2*>(slice + c * DFCSR_VOXEL_DOUBLES);
+        dst[0] = make_double2(fields[c], fields[cells + c]);
+        dst[1] = make_double2(fields[2 * cells + c], fields[3 * cells + c]);
+        dst[2] = make_double2(fields[4 * cells + c], 0.0);
+    }
+}
+
+__global__ void unpack_kernel(const double* __restrict__ slice, long long cells, double* __restrict__ fields) {
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < cells;
+         c += (long long)gridDim.x * blockDim.x) {
+        const double2* src = reinterpret_cast<const double2*>(slice + c * DFCSR_VOXEL_DOUBLES);
+        double2 a = src[0], b = src[1], d = src[2];
+        fields[c] = a.x;
+        fields[cells + c] = a.y;
+        fields[2 * cells + c] = b.x;
+        fields[3 * cells + c] = b.y;
+        fields[4 * cells + c] = d.x;
+    }
+}
+
+static inline unsigned blocks_for(long long n, int threads) {
+    long long b = (n + threads - 1) / threads;
+    const long long cap = 148LL * 16;
+    return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace dfcsr
+
+using namespace dfcsr;
+
+extern "C" int dfcsr_history_regrid(const double* d_fields, dfcsr_axis src_x, dfcsr_axis src_z,
+                                    dfcsr_axis dst_x, dfcsr_axis dst_z, double fill_vx_x,
+                                    const double* d_fill_vx_x, double* d_slice, void* stream) {
+    DFCSR_REQUIRE(d_fields && d_slice, "null pointer");
+    DFCSR_REQUIRE(src_x.n >= 2 && src_z.n >= 2 && dst_x.n >= 1 && dst_z.n >= 1, "axes too short");
+    Axis sx = make_axis(src_x.start, src_x.stop, src_x.n), sz = make_axis(src_z.start, src_z.stop, src_z.n);
+    Axis dx = make_axis(dst_x.start, dst_x.stop, dst_x.n), dz = make_axis(dst_z.start, dst_z.stop, dst_z.n);
+    dim3 grid((dz.n + kRegridCols - 1) / kRegridCols, (dx.n + kRegridRows - 1) / kRegridRows);
+    DFCSR_REQUIRE(grid.y <= 65535, "destination grid too tall");
+    regrid_kernel<<<grid, kRegridCols, 0, as_stream(stream)>>>(d_fields, sx, sz, dx, dz, fill_vx_x, d_fill_vx_x, d_slice);
+    DFCSR_CUDA_OK(cudaGetLastError());
+    return DFCSR_OK;
+}
+
+extern "C" int dfcsr_history_pack(const double* d_fields, int32_t X, int32_t Z, double* d_slice, void* stream) {
+    DFCSR_REQUIRE(d_fields && d_slice && X > 0 && Z > 0, "bad argument");
+    long long cells = (long long)X * Z;
+    pack_kernel<<<blocks_for(cells, 256), 256, 0, as_stream(stream)>>>(d_fields, cells, d_slice);
+    DFCSR_CUDA_OK(cudaGetLastError());
+    return DFCSR_OK;
+}
+
+extern "C" int dfcsr_history_unpack(const double* d_slice, int32_t X, int32_t Z, double* d_fields, void* stream) {
+    DFCSR_REQUIRE(d_fields && d_slice && X > 0 && Z > 0, "bad argument");
+    long long cells = (long long)X * Z;
+    unpack_kernel<<<blocks_for(cells, 256), 256, 0, as_stream(stream)>>>(d_slice, cells, d_fields);
+    DFCSR_CUDA_OK(cudaGetLastError());
+    return DFCSR_OK;
+}

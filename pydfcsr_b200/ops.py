@@ -1,0 +1,259 @@
+"""Functional wrappers over the C ABI (include/dfcsr_b200.h) taking torch CUDA tensors.
+
+PyTorch is used for device memory and streams only; every computation below is one of the
+hand-written sm_100a kernels in ``csrc/``.  There is no CPU fallback: a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Axis, check, lib
+
+F64 = torch.float64
+
+
+def _ptr(t: torch.Tensor | None) -> C.c_void_p:
+    if t is None:
+        return C.c_void_p(0)
+    if not t.is_cuda:
+        raise _lib.DfcsrError("pydfcsr_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise _lib.DfcsrError("tensor must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+def _f64(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != F64:
+        raise _lib.DfcsrError(f"{name} must be float64")
+    return t
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ---------------------------------------------------------------------------------------------
+# A14 beam scalars
+# ---------------------------------------------------------------------------------------------
+_stats_ws: dict = {}
+
+
+def beam_stats(x: torch.Tensor, z: torch.Tensor, pz: torch.Tensor | None = None) -> np.ndarray:
+    """Device reductions -> 16 doubles on the host (indices: ``_lib.S_*``).  Synchronises."""
+    dev = x.device
+    if dev not in _stats_ws:
+        _stats_ws[dev] = (torch.zeros(lib.dfcsr_beam_stats_workspace(), dtype=torch.uint8, device=dev),
+                          torch.zeros(_lib.STATS_DOUBLES, dtype=F64, device=dev),
+                          torch.zeros(_lib.STATS_DOUBLES, dtype=F64).pin_memory())
+    ws, d_stats, h_stats = _stats_ws[dev]
+    check(lib.dfcsr_beam_stats(_ptr(_f64(x, "x")), _ptr(_f64(z, "z")), _ptr(pz), x.numel(), _ptr(d_stats),
+                               _ptr(ws), _stream()), "dfcsr_beam_stats")
+    h_stats.copy_(d_stats, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return h_stats.numpy().copy()
+
+
+# ---------------------------------------------------------------------------------------------
+# K1 deposit
+# ---------------------------------------------------------------------------------------------
+def deposit_cic(x, z, px, nx, x_start, x_end, nz, z_start, z_end, mode=0, out=None):
+    """(count, vxsum): the two CIC grids of deposit.py:172-182 in one pass."""
+    if out is None:
+        out = torch.empty((2, nx, nz), dtype=F64, device=x.device)
+    check(lib.dfcsr_deposit_cic(_ptr(_f64(x, "x")), _ptr(_f64(z, "z")), _ptr(_f64(px, "px")), x.numel(),
+                                nx, x_start, x_end, nz, z_start, z_end, _ptr(out[0]), _ptr(out[1]), mode,
+                                _stream()), "dfcsr_deposit_cic")
+    return out[0], out[1]
+
+
+def deposit_ngp(x, z, nx, x_start, x_end, nz, z_start, z_end):
+    out = torch.empty((nx, nz), dtype=torch.int64, device=x.device)
+    check(lib.dfcsr_deposit_ngp(_ptr(_f64(x, "x")), _ptr(_f64(z, "z")), x.numel(), nx, x_start, x_end,
+                                nz, z_start, z_end, _ptr(out), _stream()), "dfcsr_deposit_ngp")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# K2 density functions
+# ---------------------------------------------------------------------------------------------
+_sg_cache: dict = {}
+
+
+def savgol_operators(window: int, order: int):
+    """Host fp64 Savitzky-Golay operators for scipy's mode='interp' (see csrc/make_df.cu)."""
+    key = (window, order)
+    if key not in _sg_cache:
+        if window % 2 != 1 or window < 1 or order >= window:
+            raise ValueError("filter_window must be odd, positive and larger than filter_order")
+        half = window // 2
+        pos = np.arange(window, dtype=np.float64)
+        pinv = np.linalg.pinv(np.vander(pos, order + 1, increasing=True))
+        taps = (np.vander(np.array([float(half)]), order + 1, increasing=True) @ pinv)[0]
+        lo = np.vander(pos[:half], order + 1, increasing=True) @ pinv if half else np.zeros((0, window))
+        hi = np.vander(pos[window - half:], order + 1, increasing=True) @ pinv if half else np.zeros((0, window))
+        _sg_cache[key] = tuple(np.ascontiguousarray(a, dtype=np.float64) for a in (taps, lo, hi))
+    return _sg_cache[key]
+
+
+_df_ws: dict = {}
+
+
+def make_df(count, vxsum, x_axis: Axis, z_axis: Axis, window: int, order: int, velocity_threshold: float,
+            out: torch.Tensor | None = None):
+    """(fields[5, nx, nz], scalars[8]) from the deposit grids (deposit.py:183-235)."""
+    nx, nz = x_axis.n, z_axis.n
+    dev = count.device
+    need = lib.dfcsr_make_df_workspace(nx, nz)
+    ws = _df_ws.get(dev)
+    if ws is None or ws.numel() < need:
+        ws = _df_ws[dev] = torch.empty(need, dtype=torch.uint8, device=dev)
+    if out is None:
+        out = torch.empty((5, nx, nz), dtype=F64, device=dev)
+    scalars = torch.empty(_lib.DF_SCALARS, dtype=F64, device=dev)
+    taps, lo, hi = savgol_operators(window, order)
+    check(lib.dfcsr_make_df(_ptr(count), _ptr(vxsum), x_axis, z_axis, window,
+                            taps.ctypes.data_as(C.c_void_p), lo.ctypes.data_as(C.c_void_p),
+                            hi.ctypes.data_as(C.c_void_p), float(velocity_threshold), _ptr(out), _ptr(scalars),
+                            _ptr(ws), _stream()), "dfcsr_make_df")
+    return out, scalars
+
+
+# ---------------------------------------------------------------------------------------------
+# K3 history
+# ---------------------------------------------------------------------------------------------
+def history_regrid(fields, src_x: Axis, src_z: Axis, dst_x: Axis, dst_z: Axis, fill_vx_x, slice_out):
+    """fill_vx_x: host float, or a 1-element CUDA tensor (read on the device, no host sync)."""
+    dev_fill = fill_vx_x if isinstance(fill_vx_x, torch.Tensor) else None
+    check(lib.dfcsr_history_regrid(_ptr(fields), src_x, src_z, dst_x, dst_z,
+                                   0.0 if dev_fill is not None else float(fill_vx_x), _ptr(dev_fill),
+                                   _ptr(slice_out), _stream()), "dfcsr_history_regrid")
+    return slice_out
+
+
+def history_pack(fields, slice_out=None):
+    _, X, Z = fields.shape
+    if slice_out is None:
+        slice_out = torch.empty((X, Z, _lib.VOXEL_DOUBLES), dtype=F64, device=fields.device)
+    check(lib.dfcsr_history_pack(_ptr(_f64(fields, "fields")), X, Z, _ptr(slice_out), _stream()), "dfcsr_history_pack")
+    return slice_out
+
+
+def history_unpack(slice_in, X, Z):
+    out = torch.empty((5, X, Z), dtype=F64, device=slice_in.device)
+    check(lib.dfcsr_history_unpack(_ptr(slice_in), X, Z, _ptr(out), _stream()), "dfcsr_history_unpack")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# K4 wake
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class DeviceLattice:
+    """Lattice tables uploaded once per run (lattice.py:136-143)."""
+    table: torch.Tensor       # (ns, 6)
+    rho: torch.Tensor
+    distance: torch.Tensor
+    min_s: float
+    delta_s: float
+
+    @classmethod
+    def upload(cls, coords, n_vec, tau_vec, rho, distance, min_s, delta_s, device):
+        tab = np.concatenate([np.asarray(coords, dtype=np.float64), np.asarray(n_vec, dtype=np.float64),
+                              np.asarray(tau_vec, dtype=np.float64)], axis=1)
+        return cls(torch.from_numpy(np.ascontiguousarray(tab)).to(device),
+                   torch.from_numpy(np.ascontiguousarray(rho, dtype=np.float64)).to(device),
+                   torch.from_numpy(np.ascontiguousarray(distance, dtype=np.float64)).to(device),
+                   float(min_s), float(delta_s))
+
+    def view(self) -> _lib.Lattice:
+        return _lib.Lattice(self.table.data_ptr(), self.table.shape[0], self.rho.numel(), self.min_s, self.delta_s,
+                            self.rho.data_ptr(), self.distance.data_ptr())
+
+
+@dataclass
+class DeviceHistory:
+    """Device-resident (t', x, z) history ring of 48-byte voxels."""
+    ring: torch.Tensor        # (cap, X, Z, 6)
+    head: int
+    T: int
+    min_t: float
+    min_x: float
+    min_z: float
+    delta_t: float
+    delta_x: float
+    delta_z: float
+
+    def view(self) -> _lib.History:
+        cap, X, Z, _ = self.ring.shape
+        return _lib.History(self.ring.data_ptr(), X * Z * _lib.VOXEL_DOUBLES, cap, self.head, self.T, X, Z, 0,
+                            self.min_t, self.min_x, self.min_z, self.delta_t, self.delta_x, self.delta_z)
+
+    @classmethod
+    def from_stacks(cls, stacks, min_t, min_x, min_z, delta_t, delta_x, delta_z, device, cap=None, head=0):
+        """Import five host (T, X, Z) arrays in dfcsr_field order (oracle / golden histories)."""
+        T, X, Z = stacks[0].shape
+        cap = cap or T
+        ring = torch.zeros((cap, X, Z, _lib.VOXEL_DOUBLES), dtype=F64, device=device)
+        for k in range(T):
+            fields = torch.from_numpy(np.ascontiguousarray(np.stack([s[k] for s in stacks]))).to(device)
+            history_pack(fields, ring[(head + k) % cap])
+        return cls(ring, head, T, float(min_t), float(min_x), float(min_z), float(delta_t), float(delta_x),
+                   float(delta_z))
+
+
+def wake_params(t, sigma_x, sigma_z, slope0, mean_x, formation_window, csr_scaling, nx, nz) -> _lib.WakeParams:
+    return _lib.WakeParams(float(t), float(sigma_x), float(sigma_z), float(slope0), float(mean_x),
+                           float(formation_window), float(csr_scaling), int(nx), int(nz))
+
+
+def wake_mesh(hist: DeviceHistory, lat: DeviceLattice, wp: _lib.WakeParams, xmesh, zmesh, first=0, count=None,
+              out=None, counters=None):
+    """(dE_dct, x_kick) for mesh points [first, first+count) (CSR.py:397-451)."""
+    count = xmesh.numel() - first if count is None else count
+    if out is None:
+        out = torch.empty((2, max(count, 1)), dtype=F64, device=xmesh.device)
+    hv, lv = hist.view(), lat.view()
+    check(lib.dfcsr_wake_mesh(C.byref(hv), C.byref(lv), C.byref(wp), _ptr(_f64(xmesh, "xmesh")),
+                              _ptr(_f64(zmesh, "zmesh")), first, count, _ptr(out[0]), _ptr(out[1]),
+                              _ptr(counters), _stream()), "dfcsr_wake_mesh")
+    return out[0][:count], out[1][:count]
+
+
+def wake_point_debug(hist: DeviceHistory, lat: DeviceLattice, wp: _lib.WakeParams, s: float, x: float):
+    """Integrand arrays of one point, region by region (get_CSR_wake(debug=True), CSR.py:571-600)."""
+    cap = 5 * wp.nx * wp.nz
+    iz = torch.zeros(cap, dtype=F64, device=hist.ring.device)
+    ix = torch.zeros(cap, dtype=F64, device=hist.ring.device)
+    regions = np.zeros((4, 6))
+    nreg = C.c_int32(0)
+    hv, lv = hist.view(), lat.view()
+    check(lib.dfcsr_wake_point_debug(C.byref(hv), C.byref(lv), C.byref(wp), float(s), float(x), _ptr(iz), _ptr(ix),
+                                     cap, regions.ctypes.data_as(C.c_void_p), C.byref(nreg), _stream()),
+          "dfcsr_wake_point_debug")
+    out = []
+    base = 0
+    izh, ixh = iz.cpu().numpy(), ix.cpu().numpy()
+    for r in range(nreg.value):
+        n_x, n_s = int(regions[r, 2]), int(regions[r, 5])
+        out.append(dict(xp=np.linspace(regions[r, 0], regions[r, 1], n_x), sp=np.linspace(regions[r, 3], regions[r, 4], n_s),
+                        integrand_z=izh[base:base + n_x * n_s].reshape(n_x, n_s),
+                        integrand_x=ixh[base:base + n_x * n_s].reshape(n_x, n_s)))
+        base += n_x * n_s
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# K5 kick
+# ---------------------------------------------------------------------------------------------
+def apply_kick(x, z, px, pz, slope, intercept, dE, kick, x_axis: Axis, z_axis: Axis, step_size, init_energy,
+               transverse_on=True):
+    """In-place px/pz update (beams.py:108-131)."""
+    check(lib.dfcsr_apply_kick(_ptr(_f64(x, "x")), _ptr(_f64(z, "z")), _ptr(_f64(px, "px")), _ptr(_f64(pz, "pz")),
+                               x.numel(), float(slope), float(intercept), _ptr(_f64(dE, "dE")), _ptr(_f64(kick, "kick")),
+                               x_axis, z_axis, float(step_size), float(init_energy), int(bool(transverse_on)),
+                               _stream()), "dfcsr_apply_kick")

@@ -45,3 +45,30 @@ def gaussian_bunch(n_particle: int, seed: int = 0, tilt: float = 0.0, modulation
     if tilt:
         x = x + tilt * z
     return np.ascontiguousarray(np.stack([x, px, y, py, z, pz]))
+
+
+# The reference's bundled 4-dipole chicane (example/input/chicane_lattice.yaml), restated as data:
+# (name, type, L [m], angle [rad], E1, E2, nsep); step_size 0.1 m.
+CHICANE_STEP = 0.1
+CHICANE_ELEMENTS = [
+    ("D0", "drift", 0.1, 0.0, 0.0, 0.0, 1),
+    ("B1", "dipole", 0.5002, 0.0483, 0.0, 0.0483, 1),
+    ("D1", "drift", 5.0058, 0.0, 0.0, 0.0, 5),
+    ("B2", "dipole", 0.5002, -0.0483, -0.0483, 0.0, 1),
+    ("D2", "drift", 1.0, 0.0, 0.0, 0.0, 1),
+    ("B3", "dipole", 0.5002, -0.0483, 0.0, -0.0483, 1),
+    ("D3", "drift", 5.0058, 0.0, 0.0, 0.0, 5),
+    ("B4", "dipole", 0.5002, 0.0483, 0.0483, 0.0, 1),
+    ("Df", "drift", 0.2, 0.0, 0.0, 0.0, 1),
+]
+
+
+def chicane_lattice_config(step_size: float = CHICANE_STEP, elements=None) -> dict:
+    """Lattice dictionary in the reference's YAML schema (lattice.py:118-135)."""
+    cfg = {"step_size": step_size}
+    for name, kind, length, angle, e1, e2, nsep in (elements or CHICANE_ELEMENTS):
+        ent = {"type": kind, "L": length, "nsep": nsep}
+        if kind == "dipole":
+            ent.update(angle=angle, E1=e1, E2=e2)
+        cfg[name] = ent
+    return cfg

@@ -1,0 +1,202 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (ctypes) against the CPU oracle on the same
+seeded inputs.  Tolerances: fp64 wakes/kicks 1e-10 relative (BASELINE.json north_star); integer
+NGP counts and the re-gridding arithmetic bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import dfcsr_oracle as O
+from tests import scenario
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import torch
+    return torch.device("cuda:0")
+
+
+def _up(a, dev):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+
+
+@pytest.mark.parametrize("tilt", [0.0, 2.5])
+def test_beam_stats(dev, tilt):
+    from pydfcsr_b200 import _lib, ops, synth
+    b = synth.gaussian_bunch(300_001, seed=3, tilt=tilt)
+    x, z, pz = b[0], b[4], b[5]
+    st = ops.beam_stats(_up(x, dev), _up(z, dev), _up(pz, dev))
+    slope = np.polyfit(z, x, 1)
+    xt = x - np.polyval(slope, z)
+    sl = np.abs(z) < 0.1 * np.std(z)
+    exp = {_lib.S_MEAN_X: np.mean(x), _lib.S_MEAN_Z: np.mean(z), _lib.S_SIGMA_X: np.std(x), _lib.S_SIGMA_Z: np.std(z),
+           _lib.S_SLOPE: slope[0], _lib.S_INTERCEPT: slope[1], _lib.S_SIGMA_XT: np.std(xt),
+           _lib.S_SLICE_SIGMA_X: np.std(x[sl]), _lib.S_SLICE_COUNT: sl.sum(), _lib.S_SIGMA_PZ: np.std(pz),
+           _lib.S_MEAN_PZ: np.mean(pz), _lib.S_N: x.size}
+    for k, v in exp.items():
+        assert abs(st[k] - v) <= 1e-11 * max(abs(v), 1e-30) + 1e-24, (k, st[k], v)
+    assert abs(st[_lib.S_MEAN_XT]) < 1e-12 * np.std(x)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("shape", [(100, 100), (37, 53)])
+def test_deposit_cic(dev, mode, shape):
+    from pydfcsr_b200 import ops, synth
+    b = synth.gaussian_bunch(200_000, seed=5)
+    x, px, z = b[0], b[1], b[4]
+    nx, nz = shape
+    # a grid narrower than the bunch so that edge guards and far-away particles are exercised
+    xs, xe = np.mean(x) - 2.5 * np.std(x), np.mean(x) + 3.0 * np.std(x)
+    zs, ze = np.mean(z) - 5 * np.std(z), np.mean(z) + 5 * np.std(z)
+    cnt, vxs = ops.deposit_cic(_up(x, dev), _up(z, dev), _up(px, dev), nx, xs, xe, nz, zs, ze, mode=mode)
+    ref_c = O.cic_deposit_2d(x, z, np.ones_like(x), nx, xs, xe, nz, zs, ze)
+    ref_v = O.cic_deposit_2d(x, z, px, nx, xs, xe, nz, zs, ze)
+    assert _rel(cnt.cpu().numpy(), ref_c) < 1e-12
+    assert _rel(vxs.cpu().numpy(), ref_v) < 1e-11   # signed weights: compare against max |.|
+
+
+def test_deposit_cic_empty_and_single(dev):
+    import torch
+    from pydfcsr_b200 import ops
+    e = torch.empty(0, dtype=torch.float64, device=dev)
+    cnt, vxs = ops.deposit_cic(e, e, e, 8, 0.0, 1.0, 8, 0.0, 1.0)
+    assert float(cnt.abs().sum()) == 0.0 and float(vxs.abs().sum()) == 0.0
+    one = _up([0.5], dev)
+    cnt, _ = ops.deposit_cic(one, one, one, 8, 0.0, 1.0, 8, 0.0, 1.0)
+    ref = O.cic_deposit_2d(np.array([0.5]), np.array([0.5]), np.ones(1), 8, 0.0, 1.0, 8, 0.0, 1.0)
+    assert np.array_equal(cnt.cpu().numpy(), ref)
+
+
+def test_deposit_ngp_bit_exact(dev):
+    from pydfcsr_b200 import ops, synth
+    b = synth.gaussian_bunch(500_000, seed=7)
+    x, z = b[0], b[4]
+    args = (64, np.mean(x) - 3 * np.std(x), np.mean(x) + 3 * np.std(x), 128, np.mean(z) - 3 * np.std(z), np.mean(z) + 3 * np.std(z))
+    got = ops.deposit_ngp(_up(x, dev), _up(z, dev), *args).cpu().numpy()
+    ref = O.ngp_deposit_2d(x, z, *args)
+    assert got.dtype == np.int64 and np.array_equal(got, ref)
+    assert got.sum() < x.size            # some particles fall outside the 3-sigma grid
+
+
+@pytest.mark.parametrize("tilt,order,window", [(0.0, 1, 9), (2.5, 1, 9), (2.5, 2, 9), (2.5, 0, 5), (0.0, 0, 0)])
+def test_make_df(dev, tilt, order, window):
+    from pydfcsr_b200 import ops, synth
+    from pydfcsr_b200._lib import Axis
+    b = synth.gaussian_bunch(200_000, seed=11, tilt=tilt)
+    x, px, z = b[0], b[1], b[4]
+    cfg = O.DepositConfig(xbins=64, zbins=96, filter_order=order, filter_window=window, velocity_threhold=1000)
+    df = O.make_density_functions(x, z, px, 0.0, cfg)
+    nx, nz = df.density.shape
+    win = window if (nx, nz) == (64, 96) else 5
+    xs, xe, zs, ze = df.x_grids[0], df.x_grids[-1], df.z_grids[0], df.z_grids[-1]
+    cnt = O.cic_deposit_2d(x, z, np.ones_like(x), nx, xs, xe, nz, zs, ze)
+    vxs = O.cic_deposit_2d(x, z, px, nx, xs, xe, nz, zs, ze)
+    fields, scal = ops.make_df(_up(cnt, dev), _up(vxs, dev), Axis.make(xs, xe, nx), Axis.make(zs, ze, nz), win, order, 1000)
+    f = fields.cpu().numpy()
+    for k, name in enumerate(O.FIELDS):
+        assert _rel(f[k], getattr(df, name)) < 1e-11, name
+    assert abs(float(scal[4]) - np.mean(df.vx_x)) <= 1e-11 * np.max(np.abs(df.vx_x))
+
+
+def test_history_regrid_bit_exact(dev):
+    from pydfcsr_b200 import ops
+    from pydfcsr_b200._lib import Axis
+    import torch
+    rng = np.random.default_rng(0)
+    src = rng.normal(size=(5, 41, 57))
+    sx, sz = np.linspace(-1.3e-4, 2.1e-4, 41), np.linspace(-9e-4, 1.1e-3, 57)
+    # destination wider than the source on one side, inside on the other, and hitting source nodes exactly
+    dx, dz = np.linspace(-2.0e-4, 2.1e-4, 333), np.linspace(-9e-4, 0.9e-3, 250)
+    out = torch.empty((333, 250, 6), dtype=torch.float64, device=dev)
+    ops.history_regrid(_up(src, dev), Axis.make(sx[0], sx[-1], 41), Axis.make(sz[0], sz[-1], 57),
+                       Axis.make(dx[0], dx[-1], 333), Axis.make(dz[0], dz[-1], 250), 0.125, out)
+    got = out.cpu().numpy()
+    for k in range(5):
+        ref = O.regrid_bilinear(src[k], sx, sz, dx, dz, 0.125 if k == 4 else 0.0)
+        assert np.array_equal(got[..., k], ref), k
+    assert not got[..., 5].any()
+    back = ops.history_unpack(out, 333, 250).cpu().numpy()
+    assert np.array_equal(back, np.moveaxis(got[..., :5], -1, 0))
+
+
+def _device_problem(sc, dev, nx, nz):
+    from pydfcsr_b200 import ops
+    st, lat = sc["stack"], sc["lattice"]
+    hist = ops.DeviceHistory.from_stacks([st.data[k] for k in O.FIELDS], st.min_x, st.min_y, st.min_z,
+                                         st.delta_x, st.delta_y, st.delta_z, dev, cap=st.shape[0] + 3, head=2)
+    dlat = ops.DeviceLattice.upload(lat.coords, lat.n_vec, lat.tau_vec, lat.rho, lat.distance, lat.min_s, lat.delta_s, dev)
+    wp = ops.wake_params(nx=nx, nz=nz, **sc["wake_scalars"])
+    osc = O.WakeScalars(nx=nx, nz=nz, **sc["wake_scalars"])
+    return hist, dlat, wp, osc
+
+
+@pytest.mark.parametrize("tilt", [0.0, 2.5, -2.5])
+def test_wake_mesh_matches_oracle(dev, tilt):
+    from pydfcsr_b200 import ops
+    sc = scenario.chicane_entry(tilt=tilt)
+    nx = nz = 50
+    hist, dlat, wp, osc = _device_problem(sc, dev, nx, nz)
+    x, z = sc["coords"][0], sc["coords"][4]
+    s = sc["scalars"]
+    xm, zm, _, _ = O.observation_mesh(x, z, s["slope"], s["sigma_z"], s["mean_z"], 3, 3, 5, 7)
+    import torch
+    cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+    de, kick = ops.wake_mesh(hist, dlat, wp, _up(xm, dev), _up(zm, dev), counters=cnt)
+    ref_de, ref_kick = O.wake_mesh(xm, zm, osc, sc["lattice"], sc["stack"])
+    assert _rel(de.cpu().numpy(), ref_de) < TOL
+    assert _rel(kick.cpu().numpy(), ref_kick) < TOL
+    big = np.abs(ref_de) > 1e-3 * np.max(np.abs(ref_de))
+    assert np.max(np.abs(de.cpu().numpy()[big] / ref_de[big] - 1)) < 1e-9
+    n_in, n_all = (int(v) for v in cnt.cpu())
+    assert n_all == xm.size * (4 if abs(tilt) <= 1 else 5) * nx * nz and 0 < n_in < n_all
+    # block split (CSR.py:121-125): any contiguous block gives the same numbers
+    de2, _ = ops.wake_mesh(hist, dlat, wp, _up(xm, dev), _up(zm, dev), first=11, count=9)
+    assert np.array_equal(de2.cpu().numpy(), de.cpu().numpy()[11:20])
+
+
+@pytest.mark.parametrize("tilt", [0.0, 2.5])
+def test_wake_point_debug_integrands(dev, tilt):
+    from pydfcsr_b200 import ops
+    sc = scenario.chicane_entry(tilt=tilt)
+    nx = nz = 24
+    hist, dlat, wp, osc = _device_problem(sc, dev, nx, nz)
+    s = sc["pos"] + 0.3 * sc["wake_scalars"]["sigma_z"]
+    x = 0.4 * sc["wake_scalars"]["sigma_x"]
+    got = ops.wake_point_debug(hist, dlat, wp, s, x)
+    regions = O.wake_regions(s, x, osc)
+    assert len(got) == len(regions)
+    for g, (xa, xb, n_x, sa, sb, n_s) in zip(got, regions):
+        xn, sn = np.linspace(xa, xb, n_x), np.linspace(sa, sb, n_s)
+        assert np.array_equal(g["xp"], xn) and np.array_equal(g["sp"], sn)
+        xm, sm = np.meshgrid(xn, sn, indexing="ij")
+        iz, ix = O.wake_integrand(s, x, osc, sc["lattice"], sc["stack"], xm.ravel(), sm.ravel())
+        assert _rel(g["integrand_z"].ravel(), iz) < 1e-11
+        assert _rel(g["integrand_x"].ravel(), ix) < 1e-11
+
+
+def test_apply_kick(dev):
+    from pydfcsr_b200 import ops, synth
+    from pydfcsr_b200._lib import Axis
+    b = synth.gaussian_bunch(200_000, seed=13, tilt=0.7)
+    x, px, z, pz = b[0], b[1], b[4], b[5]
+    rng = np.random.default_rng(2)
+    slope = np.polyfit(z, x, 1)
+    xt = x - np.polyval(slope, z)
+    xr = np.linspace(np.mean(xt) - 3 * np.std(xt), np.mean(xt) + 3 * np.std(xt), 10)
+    zr = np.linspace(np.mean(z) - 3 * np.std(z), np.mean(z) + 3 * np.std(z), 30)
+    de, kick = rng.normal(size=(10, 30)), rng.normal(size=(10, 30))
+    ref_px, ref_pz = O.apply_kick(x, z, px, pz, de, kick, xr, zr, 0.1, 5e9, True)
+    dpx, dpz = _up(px, dev), _up(pz, dev)
+    ops.apply_kick(_up(x, dev), _up(z, dev), dpx, dpz, slope[0], slope[1], _up(de, dev), _up(kick, dev),
+                   Axis.make(xr[0], xr[-1], 10), Axis.make(zr[0], zr[-1], 30), 0.1, 5e9, True)
+    assert _rel(dpz.cpu().numpy() - pz, ref_pz - pz) < 1e-10
+    assert _rel(dpx.cpu().numpy() - px, ref_px - px) < 1e-10
+    assert np.count_nonzero(ref_pz == pz) > 0     # particles outside the 3-sigma mesh get no kick
+    assert np.array_equal((dpz.cpu().numpy() == pz), (ref_pz == pz))
