@@ -105,6 +105,8 @@ typedef struct dfcsr_wake_params {
 
 int dfcsr_abi_version(void);
 const char* dfcsr_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench accounting) */
+int64_t dfcsr_launch_count(void);
 
 /* ---- A14 beam scalars (beams.py:88-98,137-156,201-215; deposit.py:147-159) --------------------
  * Three reduction passes over (x, z[, pz]); results land in d_stats[DFCSR_STATS_DOUBLES].

@@ -57,6 +57,7 @@ _L = C.c_int64
 SIGNATURES = {
     "dfcsr_abi_version": (C.c_int, []),
     "dfcsr_last_error": (C.c_char_p, []),
+    "dfcsr_launch_count": (_L, []),
     "dfcsr_beam_stats_workspace": (_L, []),
     "dfcsr_beam_stats": (C.c_int, [_P, _P, _P, _L, _P, _P, _P]),
     "dfcsr_deposit_cic": (C.c_int, [_P, _P, _P, _L, _I, _D, _D, _I, _D, _D, _P, _P, _I, _P]),

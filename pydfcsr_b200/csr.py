@@ -1,0 +1,342 @@
+"""``CSR2D`` driver: the reference's orchestration (CSR.py:27-879) kept in Python, with the hot path
+behind it running on the B200.
+
+Same construction (`CSR2D(input_file, parallel)`), same YAML schema and defaults, same public
+methods and result attributes:
+
+    run(stop_time, debug)          CSR.py:202   element loop / step splitting / formation length
+    get_CSR_mesh()                 CSR.py:361   -> CSR_xmesh, CSR_zmesh, CSR_zrange, CSR_xrange_transformed
+    calculate_2D_CSR()             CSR.py:397   -> dE_dct, x_kick  (one K4 launch)
+    calculate_2D_CSR_parallel()    CSR.py:420   mesh sharded with the reference's MPI block split,
+                                                NCCL all-gather in place of the two Allgatherv calls
+    get_CSR_wake(s, x, debug)      CSR.py:454   single point / integrand arrays
+
+`parallel=True` expects one process per GPU under torchrun (RANK/LOCAL_RANK/WORLD_SIZE), replacing
+`mpirun -n P python -m pyDFCSR_mpi_run` (pyDFCSR_mpi_run.py).  Every rank replicates tracking,
+deposition and history exactly as every MPI rank does in the reference (CSR.py:202-307).
+"""
+from __future__ import annotations
+
+import datetime
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import distributed as dist_utils
+from . import ops, tracking
+from .beams import Beam
+from .deposit import DF_tracker
+from .lattice import Lattice
+from .params import CSR_params, Integration_params
+from .yaml_parser import full_path, parse_yaml
+
+
+def isotime():
+    return datetime.datetime.now(datetime.timezone.utc).astimezone().replace(microsecond=0).isoformat().replace(":", "_")
+
+
+class CSR2D:
+    def __init__(self, input_file=None, parallel=False, device=None, verbose=True):
+        self.timestamp = isotime()
+        self.verbose = verbose
+        self.parallel = bool(parallel)
+        if self.parallel:
+            self.init_MPI()
+        else:
+            self.rank, self.world_size = 0, 1
+        if device is None:
+            device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)) if self.parallel else torch.cuda.current_device())
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        if input_file is not None:
+            self.parse_input(input_file)
+            self.input_file = input_file
+        self.formation_length = None
+        self.initialization()
+        self.prefix = f"{self.CSR_params.write_name}-{self.timestamp}"
+        if self.parallel:
+            self._split_mesh()
+
+    # ------------------------------------------------------------------------------- input
+    def parse_input(self, input_file):
+        inp = parse_yaml(input_file)
+        self.check_input_consistency(inp)
+        self.input = inp
+        self.beam = Beam(inp["input_beam"], device=self.device)
+        self.lattice = Lattice(inp["input_lattice"])
+        self.DF_tracker = DF_tracker(inp.get("particle_deposition"), device=self.device)
+        self.integration_params = Integration_params(inp.get("CSR_integration"))
+        self.CSR_params = CSR_params(inp.get("CSR_computation"))
+
+    def check_input_consistency(self, inp):
+        self.required_inputs = ["input_beam", "input_lattice"]
+        allowed = self.required_inputs + ["particle_deposition", "distribution_interpolation", "CSR_integration",
+                                          "CSR_computation"]
+        for key in inp:
+            assert key in allowed, f"Incorrect param given to CSR2D.__init__(**kwargs): {key}\nAllowed params: {allowed}"
+        for req in self.required_inputs:
+            assert req in inp, f"Required input parameter {req} to CSR2D.__init__(**kwargs) was not found."
+
+    def initialization(self):
+        """Deposit the initial beam (CSR.py:70-81)."""
+        b = self.beam
+        self.DF_tracker.get_DF(x=b.x, z=b.z, px=b.px, t=b.position, stats=b.stats)
+        self.DF_tracker.append_DF()
+        self.DF_tracker.append_interpolant(formation_length=float("inf"),
+                                           n_formation_length=self.integration_params.n_formation_length)
+        self.CSR_scaling = 8.98755e3 * b.charge
+        self.init_statistics()
+
+    def init_statistics(self):
+        n = self.lattice.total_steps
+        keys = ["alpha", "beta", "gamma", "emit", "eta", "etap", "norm_emit"]
+        self.statistics = {"twiss": {f"{k}_{p}": np.zeros(n) for p in ("x", "y") for k in keys},
+                           "slope": np.zeros((n, 2))}
+        for k in ("sigma_x", "sigma_z", "sigma_energy", "mean_x", "mean_z", "mean_energy"):
+            self.statistics[k] = np.zeros(n)
+        self.update_statistics(step=0)
+        self.inbend = False
+        self.afterbend = False
+        self.R_rec = None
+        self.phi_rec = None
+
+    def update_statistics(self, step):
+        if step >= self.lattice.total_steps:
+            return
+        tw = self.beam.twiss
+        for k, v in tw.items():
+            self.statistics["twiss"][k][step] = v
+        b = self.beam
+        self.statistics["slope"][step, :] = b._slope
+        self.statistics["sigma_x"][step] = b._sigma_x
+        self.statistics["sigma_z"][step] = b._sigma_z
+        self.statistics["sigma_energy"][step] = b.sigma_energy
+        self.statistics["mean_x"][step] = b._mean_x
+        self.statistics["mean_z"][step] = b._mean_z
+        self.statistics["mean_energy"][step] = b.mean_energy
+
+    # ------------------------------------------------------------------------------- multi-GPU
+    def init_MPI(self):
+        """Name kept from the reference (CSR.py:116-125); the communicator is torch.distributed/NCCL."""
+        self.rank, self.world_size = dist_utils.init_process_group()
+
+    def _split_mesh(self):
+        n = self.CSR_params.xbins * self.CSR_params.zbins
+        self.count, displ = dist_utils.split_counts(n, self.world_size)
+        self.displ = np.array(displ)
+
+    # ------------------------------------------------------------------------------- run loop
+    def get_formation_length(self, R, sigma_z, phi=0.0, inbend=True):
+        if inbend:
+            self.formation_length = (24 * (R ** 2) * sigma_z) ** (1 / 3)
+        else:
+            self.formation_length = (3 * R ** 2 * phi ** 4) / (4 * (-6 * sigma_z + R * phi ** 3))
+
+    def get_bmadx_element(self, ele, DL, entrance=False, exit=False):
+        """Element for one (partial) step (CSR.py:146-199); returns a `tracking` stand-in element."""
+        cfg = dict(self.lattice.lattice_config[ele])
+        kind = cfg["type"]
+        if kind == "dipole":
+            L = cfg["L"]
+            G = cfg["G"] if "G" in cfg else cfg["angle"] / L
+            E1, E2 = cfg.get("E1", 0), cfg.get("E2", 0)
+            if entrance and exit:
+                return tracking.SBend(L=DL, G=G, E1=E1, E2=E2, FRINGE_AT=cfg.get("FRINGE_AT", "both_ends"))
+            if entrance:
+                return tracking.SBend(L=DL, G=G, E1=E1, E2=0.0, FRINGE_AT="entrance_end")
+            if exit:
+                return tracking.SBend(L=DL, G=G, E1=0.0, E2=E2, FRINGE_AT="exit_end")
+            return tracking.SBend(L=DL, G=G, E1=0.0, E2=0.0, FRINGE_AT="no_end")
+        if kind == "quad":
+            return tracking.Quadrupole(L=DL, K1=cfg["K1"])
+        if kind == "sextupole":
+            return tracking.Sextupole(L=DL, K2=cfg["K2"])
+        return tracking.Drift(L=DL)
+
+    def _log(self, *a):
+        if self.verbose and self.rank == 0:
+            print(*a)
+
+    def hot_path_step(self, apply=True, kick_length=None):
+        """One pass of the ★ path at the current beam state (CSR.py:299-307, 324-334): deposit,
+        history push, mesh, wake, kick.  Returns nothing; results in dE_dct / x_kick."""
+        kick_length = self.lattice.step_size if kick_length is None else kick_length
+        b = self.beam
+        self.DF_tracker.get_DF(x=b.x, z=b.z, px=b.px, t=b.position, stats=b.stats)
+        self.DF_tracker.append_DF()
+        self.DF_tracker.append_interpolant(formation_length=self.formation_length,
+                                           n_formation_length=self.integration_params.n_formation_length)
+        self.DF_tracker.build_interpolant()
+        self.get_CSR_mesh()
+        if self.parallel:
+            self.calculate_2D_CSR_parallel()
+        else:
+            self.calculate_2D_CSR()
+        if apply:
+            b.apply_wakes(self.dE_dct, self.x_kick, self.CSR_xrange_transformed, self.CSR_zrange,
+                          kick_length, self.CSR_params.transverse_on)
+
+    def run(self, stop_time=None, debug=False):
+        self._log("Starting the DFCSR run")
+        lat, b = self.lattice, self.beam
+        step_count = 1
+        DL = lat.step_size
+        ele_count = 0
+        skip_ele = False
+        self.inbend = self.afterbend = False
+        self.formation_length = 0.0
+        ele_prev = None
+        for ele in list(lat.lattice_config.keys())[1:]:
+            lat.update(ele)
+            cfg = lat.lattice_config[ele]
+            L, kind = cfg["L"], cfg["type"]
+            steps = lat.steps_per_element[ele_count]
+            if (not skip_ele) and ele_count > 0:                           # CSR.py:228-236
+                DL_1 = lat.distance[ele_count - 1] - b.position
+                if DL_1 > 1.0e-6:
+                    b.track(self.get_bmadx_element(ele=ele_prev, DL=DL_1, exit=True), DL_1, update_step=False)
+            if steps == 0:                                                 # CSR.py:238-241
+                skip_ele = True
+                b.track(self.get_bmadx_element(ele=ele, DL=L, exit=True, entrance=True), L, update_step=False)
+            if kind == "dipole":                                           # CSR.py:246-256
+                R = L / cfg["angle"]
+                self.inbend = self.afterbend = True
+                self.R_rec, self.phi_rec = R, cfg["angle"]
+                self.get_formation_length(R=R, sigma_z=5 * b.sigma_z, inbend=True)
+            else:
+                self.inbend = False
+                if self.afterbend:
+                    self.get_formation_length(R=self.R_rec, sigma_z=5 * b.sigma_z, inbend=True)
+                else:
+                    self.formation_length += L
+            for step in range(steps):
+                t0 = time.time()
+                if step == 0 and ele_count > 0:                            # CSR.py:279-288
+                    DL_2 = lat._positions_record[step_count] - lat.distance[ele_count - 1]
+                    b.track(self.get_bmadx_element(ele=ele, DL=DL_2, entrance=True), DL_2)
+                    skip_ele = False
+                else:
+                    b.track(self.get_bmadx_element(ele=ele, DL=DL), DL)
+                if debug or self.CSR_params.compute_CSR:                   # CSR.py:297-307
+                    self.DF_tracker.get_DF(x=b.x, z=b.z, px=b.px, t=b.position, stats=b.stats)
+                    self.DF_tracker.append_DF()
+                    self.DF_tracker.append_interpolant(formation_length=self.formation_length,
+                                                       n_formation_length=self.integration_params.n_formation_length)
+                    self.DF_tracker.build_interpolant()
+                if self.CSR_params.compute_CSR and step % lat.nsep[ele_count] == 0:   # CSR.py:321-339
+                    self.get_CSR_mesh()
+                    if self.parallel:
+                        self.calculate_2D_CSR_parallel()
+                    else:
+                        self.calculate_2D_CSR()
+                    if self.CSR_params.apply_CSR:
+                        b.apply_wakes(self.dE_dct, self.x_kick, self.CSR_xrange_transformed, self.CSR_zrange,
+                                      DL * lat.nsep[ele_count], self.CSR_params.transverse_on)
+                    wb = self.CSR_params.write_beam
+                    if wb == "all" or (isinstance(wb, list) and step_count in wb):
+                        self.dump_beam(label=step_count)
+                    if self.CSR_params.write_wakes:
+                        self.write_wakes()
+                self.update_statistics(step=step_count)
+                self._log("Finish step {}, s = {},  in {} seconds".format(step_count, b.position, time.time() - t0))
+                step_count += 1
+                if stop_time and b.position > stop_time:
+                    return
+            ele_prev = ele
+            ele_count += 1
+        self.dump_beam(label="end")
+        self.write_statistics()
+
+    # ------------------------------------------------------------------------------- mesh + wake
+    def get_CSR_mesh(self):
+        """CSR.py:361-394.  The O(Np) statistics of x_transform come from the device reductions;
+        the mesh itself (<= 32768 points) is built on the host exactly as the reference does."""
+        b, p = self.beam, self.CSR_params
+        slope = b._slope
+        sig_x, mean_x = b.sigma_x_transform, b.mean_x_transform
+        zrange = np.linspace(b.mean_z - p.zlim * b.sigma_z, b.mean_z + p.zlim * b.sigma_z, p.zbins)
+        xrange = np.linspace(mean_x - p.xlim * sig_x, mean_x + p.xlim * sig_x, p.xbins)
+        xm, zm = np.meshgrid(xrange, zrange, indexing="ij")
+        zm = zm.flatten()
+        xm = xm.flatten() + np.polyval(slope, zm)
+        self.CSR_xmesh, self.CSR_zmesh = xm, zm
+        self.CSR_zrange, self.CSR_xrange_transformed = zrange, xrange
+        self._d_mesh = torch.from_numpy(np.stack([xm, zm])).to(self.device, non_blocking=True)
+
+    def _wake_params(self):
+        b, ip = self.beam, self.integration_params
+        return ops.wake_params(t=b.position, sigma_x=b._sigma_x, sigma_z=b._sigma_z, slope0=b._slope[0],
+                               mean_x=b._mean_x, formation_window=ip.n_formation_length * self.formation_length,
+                               csr_scaling=self.CSR_scaling, nx=ip.xbins, nz=ip.zbins)
+
+    def calculate_2D_CSR(self):
+        """CSR.py:397-418: the whole mesh in one launch; results stay on the device
+        (`dE_dct`, `x_kick` are (xbins, zbins) CUDA tensors; `.cpu().numpy()` for host copies)."""
+        p = self.CSR_params
+        lat = self.lattice.device_tables(self.device)
+        de, kick = ops.wake_mesh(self.DF_tracker.history, lat, self._wake_params(), self._d_mesh[0], self._d_mesh[1],
+                                 counters=getattr(self, "wake_counters", None))
+        self.dE_dct = de.reshape(p.xbins, p.zbins)
+        self.x_kick = kick.reshape(p.xbins, p.zbins)
+
+    def calculate_2D_CSR_parallel(self):
+        """CSR.py:420-451: this rank's contiguous block, then one all-gather of [dE | kick]."""
+        p = self.CSR_params
+        n = p.xbins * p.zbins
+        lat = self.lattice.device_tables(self.device)
+        pad = max(self.count)
+        send = torch.zeros((2, pad), dtype=torch.float64, device=self.device)
+        ops.wake_mesh(self.DF_tracker.history, lat, self._wake_params(), self._d_mesh[0], self._d_mesh[1],
+                      first=int(self.displ[self.rank]), count=int(self.count[self.rank]), out=send,
+                      counters=getattr(self, "wake_counters", None))
+        full = dist_utils.all_gather_blocks(send, self.count, n)
+        self.dE_dct = full[0].reshape(p.xbins, p.zbins)
+        self.x_kick = full[1].reshape(p.xbins, p.zbins)
+
+    def get_CSR_wake(self, s, x, debug=False):
+        """CSR.py:454-602 for one point.  debug=True returns the per-region node and integrand arrays
+        (list of dicts with xp, sp, integrand_z, integrand_x) like the reference's debug tuple."""
+        lat = self.lattice.device_tables(self.device)
+        wp = self._wake_params()
+        if debug:
+            return ops.wake_point_debug(self.DF_tracker.history, lat, wp, s, x)
+        pt = torch.tensor([[x], [s - self.beam.position]], dtype=torch.float64, device=self.device)
+        de, kick = ops.wake_mesh(self.DF_tracker.history, lat, wp, pt[0], pt[1])
+        return float(de[0]), float(kick[0])
+
+    # ------------------------------------------------------------------------------- output
+    # The reference writes HDF5 (CSR.py:784-879); h5py is not available offline, so the same
+    # content goes to .npz files with the same group/dataset names flattened into keys.
+    def dump_beam(self, label):
+        if self.rank != 0 or not getattr(self.CSR_params, "write_beam", None):
+            return
+        path = full_path(self.CSR_params.workdir)
+        os.makedirs(path, exist_ok=True)
+        fn = os.path.join(path, f"{self.prefix}-particles-{label}.npz")
+        np.savez(fn, coords=self.beam.to_host(), position=self.beam.position, charge=self.beam.charge,
+                 energy=self.beam.init_energy)
+        self._log("Beam at position {} is written to {}".format(self.beam.position, fn))
+
+    def write_wakes(self):
+        if self.rank != 0:
+            return
+        path = full_path(self.CSR_params.workdir)
+        os.makedirs(path, exist_ok=True)
+        step = self.beam.step
+        shape = tuple(self.dE_dct.shape)
+        np.savez(os.path.join(path, f"{self.prefix}-wakes-step_{step}.npz"),
+                 step=step, position=self.beam.position, charge=self.beam.charge,
+                 x_grids=self.CSR_xmesh.reshape(shape), z_grids=self.CSR_zmesh.reshape(shape),
+                 dE_dct=self.dE_dct.cpu().numpy(), xkicks=self.x_kick.cpu().numpy(), unit="MeV/m")
+
+    def write_statistics(self):
+        if self.rank != 0 or not self.CSR_params.write_wakes:
+            return
+        path = full_path(self.CSR_params.workdir)
+        os.makedirs(path, exist_ok=True)
+        flat = {f"twiss/{k}": v for k, v in self.statistics["twiss"].items()}
+        flat.update({k: v for k, v in self.statistics.items() if k != "twiss"})
+        np.savez(os.path.join(path, f"{self.prefix}-statistics.npz"), step_positions=self.lattice.steps_record,
+                 coords=self.lattice.coords, n_vec=self.lattice.n_vec, tau_vec=self.lattice.tau_vec, **flat)

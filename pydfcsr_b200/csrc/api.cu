@@ -1,11 +1,15 @@
 // api.cu — ABI version and thread-local error reporting for libdfcsr_b200.
 #include <stdarg.h>
+#include <atomic>
 #include <string.h>
 #include "common.cuh"
 
 namespace dfcsr {
 
 static thread_local char g_error[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -23,3 +27,4 @@ int cuda_fail(cudaError_t e, const char* where) {
 
 extern "C" int dfcsr_abi_version(void) { return DFCSR_ABI_VERSION; }
 extern "C" const char* dfcsr_last_error(void) { return dfcsr::g_error; }
+extern "C" int64_t dfcsr_launch_count(void) { return (int64_t)dfcsr::g_launches.load(std::memory_order_relaxed); }

@@ -209,6 +209,7 @@ extern "C" int dfcsr_beam_stats(const double* d_x, const double* d_z, const doub
     stats_pass1<<<blocks, kStatThreads, 0, st>>>(d_x, d_z, d_pz, n, d_stats, ws);
     stats_pass2<<<blocks, kStatThreads, 0, st>>>(d_x, d_z, d_pz, n, d_stats, ws);
     stats_pass3<<<blocks, kStatThreads, 0, st>>>(d_x, d_z, n, d_stats, ws);
+    count_launch(3);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;
 }
@@ -227,6 +228,7 @@ extern "C" int dfcsr_apply_kick(const double* d_x, const double* d_z, double* d_
     unsigned blocks = (unsigned)(want < 148LL * 8 ? want : 148LL * 8);
     apply_kick_kernel<<<blocks, 256, 0, as_stream(stream)>>>(d_x, d_z, d_px, d_pz, n, slope, intercept, d_dE,
                                                            d_kick, ax, az, factor, transverse_on);
+    count_launch(1);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;
 }

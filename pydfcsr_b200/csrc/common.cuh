@@ -9,6 +9,7 @@ namespace dfcsr {
 
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* where);
+void count_launch(int n);   // kernels launched by this library (dfcsr_launch_count)
 
 #define DFCSR_CUDA_OK(expr)                                             \
     do {                                                                \

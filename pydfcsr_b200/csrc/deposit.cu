@@ -184,10 +184,12 @@ extern "C" int dfcsr_deposit_cic(const double* d_x, const double* d_z, const dou
         long long want = (n + 1024LL * 32 - 1) / (1024LL * 32);
         unsigned blocks = (unsigned)(want < 148 ? (want < 1 ? 1 : want) : 148);
         cic_private_kernel<<<blocks, 1024, smem, st>>>(d_x, d_z, d_px, n, g, d_count, d_vxsum);
+    count_launch(1);
     } else if (mode == 2) {
         long long want = (n + 255) / 256;
         unsigned blocks = (unsigned)(want < 148LL * 8 ? want : 148LL * 8);
         cic_direct_kernel<<<blocks, 256, 0, st>>>(d_x, d_z, d_px, n, g, d_count, d_vxsum);
+    count_launch(1);
     } else {
         DFCSR_REQUIRE(false, "mode must be 0, 1 or 2");
     }
@@ -207,6 +209,7 @@ extern "C" int dfcsr_deposit_ngp(const double* d_x, const double* d_z, int64_t n
     long long want = (n + 255) / 256;
     unsigned blocks = (unsigned)(want < 148LL * 8 ? want : 148LL * 8);
     ngp_kernel<<<blocks, 256, 0, st>>>(d_x, d_z, n, g, reinterpret_cast<unsigned long long*>(d_count));
+    count_launch(1);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;
 }

@@ -136,6 +136,7 @@ extern "C" int dfcsr_history_regrid(const double* d_fields, dfcsr_axis src_x, df
     dim3 grid((dz.n + kRegridCols - 1) / kRegridCols, (dx.n + kRegridRows - 1) / kRegridRows);
     DFCSR_REQUIRE(grid.y <= 65535, "destination grid too tall");
     regrid_kernel<<<grid, kRegridCols, 0, as_stream(stream)>>>(d_fields, sx, sz, dx, dz, fill_vx_x, d_fill_vx_x, d_slice);
+    count_launch(1);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;
 }
@@ -144,6 +145,7 @@ extern "C" int dfcsr_history_pack(const double* d_fields, int32_t X, int32_t Z, 
     DFCSR_REQUIRE(d_fields && d_slice && X > 0 && Z > 0, "bad argument");
     long long cells = (long long)X * Z;
     pack_kernel<<<blocks_for(cells, 256), 256, 0, as_stream(stream)>>>(d_fields, cells, d_slice);
+    count_launch(1);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;
 }
@@ -152,6 +154,7 @@ extern "C" int dfcsr_history_unpack(const double* d_slice, int32_t X, int32_t Z,
     DFCSR_REQUIRE(d_fields && d_slice && X > 0 && Z > 0, "bad argument");
     long long cells = (long long)X * Z;
     unpack_kernel<<<blocks_for(cells, 256), 256, 0, as_stream(stream)>>>(d_slice, cells, d_fields);
+    count_launch(1);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;
 }

@@ -320,6 +320,7 @@ extern "C" int dfcsr_make_df(const double* d_count, const double* d_vxsum, dfcsr
     P.ws = ws;
     P.scratch = reinterpret_cast<double*>(reinterpret_cast<char*>(d_workspace) + sizeof(DfWorkspace));
     make_df_kernel<<<kDfCtas, kDfThreads, 0, st>>>(P);
+    count_launch(1);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;
 }

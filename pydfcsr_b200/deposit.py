@@ -160,6 +160,12 @@ class DF_tracker:
         self.sigma_z_log.pop()
         self.end_time = self.time_log[-1]
 
+    def pop_right_interpolant(self):
+        """Drop the newest slice of both the raw log and the interpolant (the ring slot is simply
+        reused by the next push).  Lets a caller re-run a step from the same history state."""
+        self.pop_right_DF()
+        self.time_interp.pop()
+
     # ------------------------------------------------------------------------------- ring
     def _slot(self, k):
         return self._ring[(self._head + k) % self._ring.shape[0]]

@@ -1,0 +1,131 @@
+"""GPU parity of the whole hot path through the reference-facing classes (DF_tracker, CSR2D, Beam):
+the same particle batches go through the CUDA pipeline and through the CPU oracle pipeline."""
+import numpy as np
+import pytest
+
+from oracle import dfcsr_oracle as O
+from tests import scenario
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.mark.parametrize("tilt", [0.0, 2.5])
+def test_df_tracker_history_matches_oracle(tilt):
+    """get_DF -> append_DF -> append_interpolant -> build_interpolant over 6 logged steps."""
+    import torch
+    from pydfcsr_b200 import DF_tracker
+    sc = scenario.chicane_entry(tilt=tilt)
+    trk = DF_tracker(dict(scenario.DEPOSIT_CFG), device="cuda:0")
+    for st in sc["steps"]:
+        x, px, y, py, z, pz = st["coords"]
+        trk.get_DF(torch.from_numpy(x).cuda(), torch.from_numpy(z).cuda(), torch.from_numpy(px).cuda(), st["pos"])
+        for name in O.FIELDS:
+            assert _rel(getattr(trk, name), getattr(st["df"], name)) < 1e-10, name
+        assert np.array_equal(trk.x_grids.shape, st["df"].x_grids.shape)
+        assert _rel(trk.x_grids, st["df"].x_grids) < 1e-13
+        trk.append_DF()
+        rebuilt = trk.append_interpolant(st["formation_length"], 1)
+        assert rebuilt == st["rebuilt"]
+    trk.build_interpolant()
+    ref = sc["stack"]
+    assert (trk.history.T,) + tuple(trk._ring.shape[1:3]) == ref.shape
+    for name in O.FIELDS:
+        assert _rel(getattr(trk, f"data_{name}_interp"), ref.data[name]) < 1e-10, name
+    for a, b in ((trk.min_x, ref.min_x), (trk.min_y, ref.min_y), (trk.min_z, ref.min_z),
+                 (trk.delta_x, ref.delta_x), (trk.delta_y, ref.delta_y), (trk.delta_z, ref.delta_z)):
+        assert abs(a - b) <= 1e-12 * max(abs(b), 1e-30)
+
+
+def test_history_window_pop_and_rebuild():
+    """Sliding window (deposit.py:265-280) and the sigma-ratio rebuild (deposit.py:321-361): a bunch
+    whose length shrinks by >2x forces a rebuild with a finer grid; a short window pops old slices."""
+    import torch
+    from pydfcsr_b200 import DF_tracker, synth
+    cfg = dict(scenario.DEPOSIT_CFG)
+    cfg["upper_limit"] = 700
+    trk = DF_tracker(cfg, device="cuda:0")
+    hist = O.HistoryOracle(O.DepositConfig(**cfg))
+    b = synth.gaussian_bunch(60_000, seed=4)
+    scale = [1.0, 0.9, 0.7, 0.45, 0.4, 0.38, 0.36, 0.35]
+    for k, sc_ in enumerate(scale):
+        x, px, z = b[0], b[1], b[4] * sc_
+        t = 0.1 * k
+        fl = float("inf") if k == 0 else 0.25
+        trk.get_DF(torch.from_numpy(x).cuda(), torch.from_numpy(np.ascontiguousarray(z)).cuda(), torch.from_numpy(px).cuda(), t)
+        trk.append_DF()
+        got = trk.append_interpolant(fl, 1)
+        hist.append(O.make_density_functions(x, z, px, t, hist.cfg))
+        exp = hist.push(fl, 1)
+        assert got == exp, k
+        assert list(trk.time_interp) == list(hist.time_interp), k
+    assert trk.rebuilds == hist.rebuilds >= 2
+    trk.build_interpolant()
+    ref = hist.stack()
+    assert (trk.history.T,) + tuple(trk._ring.shape[1:3]) == ref.shape
+    assert ref.shape[0] < len(scale) and ref.shape[2] <= 700
+    for name in O.FIELDS:
+        assert _rel(getattr(trk, f"data_{name}_interp"), ref.data[name]) < 1e-10, name
+
+
+def test_csr2d_step_matches_oracle():
+    """CSR2D end to end on the device (tracking stand-in, deposit, history, mesh, wake, kick) against
+    the oracle fed with the device's particle batches."""
+    import torch
+    from pydfcsr_b200 import CSR2D, synth
+    elements = [(n, k, L, a, e1, e2, 1) for (n, k, L, a, e1, e2, _s) in synth.CHICANE_ELEMENTS]
+    inp = {"input_beam": {"style": "synthetic", "n_particle": 100_000, "seed": 1},
+           "input_lattice": {"lattice_config": synth.chicane_lattice_config(elements=elements)},
+           "particle_deposition": dict(scenario.DEPOSIT_CFG),
+           "CSR_integration": dict(n_formation_length=1, zbins=40, xbins=40),
+           "CSR_computation": dict(compute_CSR=1, apply_CSR=1, transverse_on=1, xbins=4, zbins=6, xlim=3, zlim=3,
+                                   write_beam=None, write_wakes=False, workdir="/tmp/dfcsr_test")}
+    csr = CSR2D(inp, parallel=False, device="cuda:0", verbose=False)
+    cfg = O.DepositConfig(**scenario.DEPOSIT_CFG)
+    hist = O.HistoryOracle(cfg)
+    lat = scenario.lattice_tables()
+    assert np.array_equal(lat.coords, csr.lattice.coords) and np.array_equal(lat.tau_vec, csr.lattice.tau_vec)
+
+    def oracle_log(fl):
+        c = csr.beam.to_host()
+        hist.append(O.make_density_functions(c[0], c[4], c[1], csr.beam.position, cfg))
+        hist.push(fl, 1)
+        return c
+
+    oracle_log(float("inf"))
+    # drive the same sequence as CSR2D.run but interleave the oracle after every tracking step
+    from pydfcsr_b200 import tracking
+    steps = [(tracking.Drift(0.1), 0.1)] + [(tracking.SBend(L=0.1, G=0.0483 / 0.5002, FRINGE_AT="no_end"), None)] * 3
+    for el, fl in steps:
+        if fl is None and csr.formation_length in (None, 0.1):
+            csr.get_formation_length(R=0.5002 / 0.0483, sigma_z=5 * csr.beam.sigma_z)
+        elif fl is not None:
+            csr.formation_length = fl
+        csr.beam.track(el, 0.1)
+        c = oracle_log(csr.formation_length)
+        pre_px, pre_pz = c[1].copy(), c[5].copy()
+        csr.hot_path_step(apply=True, kick_length=0.1)
+        s = O.beam_scalars(c[0], c[4])
+        xm, zm, xr, zr = O.observation_mesh(c[0], c[4], s["slope"], s["sigma_z"], s["mean_z"], 3, 3, 4, 6)
+        assert _rel(csr.CSR_xmesh, xm) < 1e-9 and _rel(csr.CSR_zmesh, zm) < 1e-12
+        sc = O.WakeScalars(t=csr.beam.position, sigma_x=float(s["sigma_x"]), sigma_z=float(s["sigma_z"]),
+                           slope0=float(s["slope"][0]), mean_x=float(s["mean_x"]), formation_window=csr.formation_length,
+                           csr_scaling=8.98755e3 * 1e-9, nx=40, nz=40)
+        de, kick = O.wake_mesh(xm, zm, sc, lat, hist.stack())
+        assert _rel(csr.dE_dct.cpu().numpy().ravel(), de) < 1e-10
+        assert _rel(csr.x_kick.cpu().numpy().ravel(), kick) < 1e-10
+        px_new, pz_new = O.apply_kick(c[0], c[4], pre_px, pre_pz, de.reshape(4, 6), kick.reshape(4, 6), xr, zr, 0.1, 5e9, True)
+        after = csr.beam.to_host()
+        assert _rel(after[5] - pre_pz, pz_new - pre_pz) < 1e-9
+        assert _rel(after[1] - pre_px, px_new - pre_px) < 1e-9
+    # single-point entry and the debug hook agree with the mesh launch
+    k = 9
+    s_k = csr.beam.position + csr.CSR_zmesh[k]
+    de_k, kick_k = csr.get_CSR_wake(s_k, csr.CSR_xmesh[k])
+    assert abs(de_k - float(csr.dE_dct.ravel()[k])) <= 1e-12 * abs(de_k)
+    dbg = csr.get_CSR_wake(s_k, csr.CSR_xmesh[k], debug=True)
+    tot = sum(np.trapz(np.trapz(r["integrand_z"], r["xp"], axis=0), r["sp"]) for r in dbg)
+    assert abs(-csr.CSR_scaling * tot - de_k) <= 1e-10 * abs(de_k)
