@@ -304,11 +304,11 @@ def gpu_arm(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms[0])
 
+    sampler = ClockSampler(dev.index or 0).start() if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step_resident()
     counters.zero_()
     launches0 = _lib.lib.dfcsr_launch_count()
-    sampler = ClockSampler(dev.index or 0).start() if rank == 0 else None
     ms_total = timed(step_resident, args.steps, timed_k4=True)
     launches = _lib.lib.dfcsr_launch_count() - launches0
     k4_ms = float(np.mean([a.elapsed_time(b) for a, b in k4_events]))
@@ -409,15 +409,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-points-per-core", type=int, default=24, help="mesh points per host core in the cpu_baseline leg")
-    ap.add_argument("--ref-points-per-core", type=int, default=16, help="mesh points per host core per step (--impl reference)")
+    ap.add_argument("--cpu-points-per-core", type=int, default=256, help="mesh points per host core in the cpu_baseline leg")
+    ap.add_argument("--ref-points-per-core", type=int, default=256, help="mesh points per host core per step (--impl reference)")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 3 if args.steps is None else args.steps
         args.warmup = 1 if args.warmup is None else args.warmup
         reference_arm(args)
     else:
-        args.steps = 20 if args.steps is None else args.steps
+        args.steps = 100 if args.steps is None else args.steps
         args.warmup = 3 if args.warmup is None else args.warmup
         gpu_arm(args)
 

@@ -40,8 +40,9 @@ def all_gather_blocks(send: torch.Tensor, count, n: int) -> torch.Tensor:
     """send: (F, pad) with this rank's block in [:, :count[rank]].  Returns (F, n) on every rank."""
     world = dist.get_world_size()
     fields, pad = send.shape
-    recv = torch.empty((world, fields, pad), dtype=send.dtype, device=send.device)
-    dist.all_gather_into_tensor(recv, send.contiguous())
+    flat = torch.empty(world * fields * pad, dtype=send.dtype, device=send.device)
+    dist.all_gather_into_tensor(flat, send.contiguous().view(-1))
+    recv = flat.view(world, fields, pad)
     if all(c == pad for c in count):
         return recv.permute(1, 0, 2).reshape(fields, n)
     return torch.cat([recv[p, :, :count[p]] for p in range(world)], dim=1)

@@ -45,6 +45,7 @@ _stats_ws: dict = {}
 
 def beam_stats(x: torch.Tensor, z: torch.Tensor, pz: torch.Tensor | None = None) -> np.ndarray:
     """Device reductions -> 16 doubles on the host (indices: ``_lib.S_*``).  Synchronises."""
+    _ptr(x), _ptr(z)          # raises for non-CUDA tensors before anything is allocated
     dev = x.device
     if dev not in _stats_ws:
         _stats_ws[dev] = (torch.zeros(lib.dfcsr_beam_stats_workspace(), dtype=torch.uint8, device=dev),

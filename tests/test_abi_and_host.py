@@ -1,0 +1,131 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/dfcsr_b200.h declares, the
+ctypes structs match the header layout, and the host-side logic (lattice, YAML, block split,
+all-gather on gloo with world_size 2) behaves like the reference's."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "dfcsr_b200.h")
+
+
+def _declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dfcsr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pydfcsr_b200 import _lib
+    names = _declared_functions()
+    assert len(names) >= 14
+    raw = C.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in the header but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(names)
+    assert _lib.lib.dfcsr_abi_version() == _lib.ABI_VERSION
+    assert _lib.lib.dfcsr_beam_stats_workspace() > 0
+    assert _lib.lib.dfcsr_make_df_workspace(100, 100) > 6 * 100 * 100 * 8
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """Compile a tiny C program against the header and compare sizeof/offsetof with ctypes."""
+    from pydfcsr_b200 import _lib
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "dfcsr_b200.h"\nint main(void){\n'
+                   'printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(dfcsr_axis), sizeof(dfcsr_history), sizeof(dfcsr_lattice),'
+                   ' sizeof(dfcsr_wake_params), offsetof(dfcsr_history, min_t), offsetof(dfcsr_lattice, d_rho),'
+                   ' offsetof(dfcsr_wake_params, nx));return 0;}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    exp = [C.sizeof(_lib.Axis), C.sizeof(_lib.History), C.sizeof(_lib.Lattice), C.sizeof(_lib.WakeParams),
+           _lib.History.min_t.offset, _lib.Lattice.d_rho.offset, _lib.WakeParams.nx.offset]
+    assert got == exp
+
+
+def test_errors_are_reported_not_raised_across_the_abi():
+    from pydfcsr_b200 import _lib
+    rc = _lib.lib.dfcsr_deposit_cic(None, None, None, 10, 4, 0.0, 1.0, 4, 0.0, 1.0, None, None, 0, None)
+    assert rc == -1 and b"null pointer" in _lib.lib.dfcsr_last_error()
+    with pytest.raises(_lib.DfcsrError):
+        _lib.check(rc, "dfcsr_deposit_cic")
+
+
+def test_no_cpu_fallback():
+    import torch
+    from pydfcsr_b200 import _lib, ops
+    with pytest.raises(_lib.DfcsrError):
+        ops.beam_stats(torch.zeros(8, dtype=torch.float64), torch.zeros(8, dtype=torch.float64))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "pydfcsr_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            text = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), fn
+            assert "import_module(\"oracle" not in text and "/root/reference" not in text, fn
+
+
+def test_lattice_and_yaml(tmp_path):
+    import yaml
+    from oracle import dfcsr_oracle as O
+    from pydfcsr_b200 import synth
+    from pydfcsr_b200.lattice import Lattice
+    from pydfcsr_b200.yaml_parser import parse_yaml
+    path = tmp_path / "lat.yaml"
+    path.write_text(yaml.safe_dump(dict(synth.chicane_lattice_config()), sort_keys=False))
+    cfg = parse_yaml(str(path))
+    assert list(cfg.keys())[0] == "step_size" and list(cfg.keys())[1:] == [e[0] for e in synth.CHICANE_ELEMENTS]
+    lat = Lattice({"lattice_input_file": str(path)})
+    ref = O.reference_orbit([(e[1], e[2], e[3]) for e in synth.CHICANE_ELEMENTS])
+    assert np.array_equal(lat.coords, ref.coords) and np.array_equal(lat.n_vec, ref.n_vec)
+    assert np.array_equal(lat.rho, ref.rho) and np.array_equal(lat.distance, ref.distance)
+    assert lat.total_steps == 134 and lat.steps_per_element.sum() == 133          # 13.3124 m / 0.1 m
+    assert abs(lat.coords[-1, 1]) < 1e-9 and abs(lat.tau_vec[-1, 1]) < 1e-12      # chicane closes
+    with pytest.raises(FileNotFoundError):
+        parse_yaml(str(tmp_path / "missing.yaml"))
+
+
+def test_savgol_operators_match_oracle():
+    from oracle import dfcsr_oracle as O
+    from pydfcsr_b200 import ops
+    for w, o in ((5, 0), (5, 2), (9, 1), (9, 2), (1, 0)):
+        a, b = ops.savgol_operators(w, o), O.savgol_operators(w, o)
+        for p, q in zip(a, b):
+            assert np.allclose(p, q, rtol=0, atol=1e-15)
+        assert abs(a[0].sum() - 1) < 1e-14
+
+
+WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from pydfcsr_b200 import distributed as D
+rank, world = D.init_process_group("gloo")
+for n in (7, 10, 4096):
+    count, displ = D.split_counts(n, world)
+    full = np.arange(2 * n, dtype=np.float64).reshape(2, n)
+    send = torch.zeros((2, max(count)), dtype=torch.float64)
+    send[:, :count[rank]] = torch.from_numpy(full[:, displ[rank]:displ[rank] + count[rank]])
+    got = D.all_gather_blocks(send, count, n).numpy()
+    assert np.array_equal(got, full), (rank, n)
+dist.barrier()
+print("ok", rank)
+'''
+
+
+def test_all_gather_blocks_world2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", str(script), ROOT]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "ok 0" in out.stdout and "ok 1" in out.stdout

@@ -1,0 +1,142 @@
+"""Pins the oracle restatement against the UNMODIFIED reference imported from /root/reference
+(build container only; skipped where the checkout is absent, e.g. on the GPU box)."""
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import dfcsr_oracle as O
+from oracle import refstub
+from tests import scenario
+
+pytestmark = pytest.mark.reference
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def ref():
+    warnings.simplefilter("ignore")
+    return refstub.load_reference()
+
+
+def test_trilinear_and_linear_gathers(ref):
+    from pyDFCSR_2D.interp1D import interpolate1D
+    from pyDFCSR_2D.interp3D import interpolate3D
+    rng = np.random.default_rng(0)
+    data = rng.normal(size=(4, 7, 9))
+    # queries straddling every edge rule: (-1,0) extrapolation, clamp at n-1, outside, NaN
+    q = np.concatenate([rng.uniform(-1.5, 10.5, 4000), [np.nan, 3.0, 6.0, 8.0, -0.3, -1.0]])
+    t, y, z = q * 0.4, np.roll(q, 1) * 0.7, np.roll(q, 2)
+    a = O.interp3d(t, y, z, data, 0.0, 0.0, 0.0, 1.0, 1.0, 1.0)
+    b = interpolate3D(t, y, z, data, 0.0, 0.0, 0.0, 1.0, 1.0, 1.0)
+    assert np.array_equal(a, b)
+    tab = rng.normal(size=31)
+    assert np.array_equal(O.interp1d(q * 3, tab, 0.5, 0.9), interpolate1D(q * 3, tab, 0.5, 0.9))
+
+
+def test_cic(ref):
+    from pyDFCSR_2D.deposit import histogram_cic_2d
+    rng = np.random.default_rng(1)
+    x, z, w = rng.normal(size=50_000), rng.normal(size=50_000), rng.normal(size=50_000)
+    a = O.cic_deposit_2d(x, z, w, 33, -2.0, 2.5, 41, -3.0, 3.0)
+    b = histogram_cic_2d(x, z, w, 33, -2.0, 2.5, 41, -3.0, 3.0)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("window,order", [(5, 0), (5, 1), (5, 2), (9, 1), (9, 2), (7, 3)])
+def test_savgol_matches_scipy(window, order):
+    from scipy.signal import savgol_filter
+    a = np.random.default_rng(2).normal(size=(40, 55))
+    ref_ = savgol_filter(savgol_filter(a, window, order, axis=0), window, order, axis=1)
+    assert _rel(O.savgol_separable(a, window, order), ref_) < 5e-13
+
+
+def test_gradient_matches_numpy():
+    a = np.random.default_rng(3).normal(size=(30, 44))
+    xg, zg = np.linspace(-1e-4, 3e-4, 30), np.linspace(-1e-3, 1e-3, 44)
+    gx, gz = np.gradient(a, xg, zg)
+    assert np.array_equal(O.gradient_axis(a, xg, 0), gx) and np.array_equal(O.gradient_axis(a, zg, 1), gz)
+    xu = np.arange(30.0)       # bit-uniform spacing takes numpy's other branch
+    assert np.array_equal(O.gradient_axis(a, xu, 0), np.gradient(a, xu, axis=0))
+
+
+def test_regrid_matches_scipy():
+    from scipy.interpolate import RegularGridInterpolator
+    rng = np.random.default_rng(4)
+    src = rng.normal(size=(21, 17))
+    xg, zg = np.linspace(-1, 2, 21), np.linspace(0, 5, 17)
+    xq, zq = np.linspace(-1.5, 2, 64), np.linspace(0, 4.9, 50)
+    X, Z = np.meshgrid(xq, zq, indexing="ij")
+    ref_ = RegularGridInterpolator((xg, zg), src, method="linear", fill_value=0.3, bounds_error=False)((X, Z))
+    assert np.array_equal(O.regrid_bilinear(src, xg, zg, xq, zq, 0.3), ref_)
+
+
+@pytest.mark.parametrize("tilt", [0.0, 2.5])
+def test_get_df(ref, tilt):
+    from pyDFCSR_2D.deposit import DF_tracker
+    from pydfcsr_b200 import synth
+    b = synth.gaussian_bunch(150_000, seed=9, tilt=tilt)
+    tr = DF_tracker(dict(scenario.DEPOSIT_CFG))
+    tr.get_DF(b[0], b[4], b[1], 0.3)
+    df = O.make_density_functions(b[0], b[4], b[1], 0.3, O.DepositConfig(**scenario.DEPOSIT_CFG))
+    assert df.density.shape == tr.density.shape
+    for k in ("x_grids", "z_grids"):
+        assert np.array_equal(getattr(df, k), getattr(tr, k))
+    for k in O.FIELDS:
+        assert _rel(getattr(df, k), getattr(tr, k)) < 1e-13, k
+
+
+@pytest.mark.parametrize("tilt", [0.0, -2.5])
+def test_history_and_wake(ref, tilt, tmp_path):
+    import yaml
+    from pydfcsr_b200 import synth
+    lat_yaml = str(tmp_path / "lat.yaml")
+    with open(lat_yaml, "w") as fh:
+        yaml.safe_dump(dict(synth.chicane_lattice_config()), fh, sort_keys=False)
+    sc = scenario.chicane_entry(tilt=tilt)
+    csr = refstub.make_reference_csr(lat_yaml, scenario.DEPOSIT_CFG, dict(n_formation_length=1, zbins=30, xbins=30),
+                                     dict(xbins=3, zbins=4, xlim=3, zlim=3, workdir=str(tmp_path)))
+    for st in sc["steps"]:
+        x, px, y, py, z, pz = st["coords"]
+        csr.DF_tracker.get_DF(x=x, z=z, px=px, t=st["pos"])
+        csr.DF_tracker.append_DF()
+        csr.DF_tracker.append_interpolant(formation_length=st["formation_length"], n_formation_length=1)
+    csr.DF_tracker.build_interpolant()
+    tr, hs = csr.DF_tracker, sc["stack"]
+    for fld, attr in zip(O.FIELDS, ("data_density_interp", "data_density_x_interp", "data_density_z_interp",
+                                    "data_vx_interp", "data_vx_x_interp")):
+        assert _rel(hs.data[fld], getattr(tr, attr)) < 1e-13
+    assert (hs.min_x, hs.min_y, hs.min_z, hs.delta_x, hs.delta_y, hs.delta_z) == \
+           (tr.min_x, tr.min_y, tr.min_z, tr.delta_x, tr.delta_y, tr.delta_z)
+    lat = sc["lattice"]
+    assert np.array_equal(lat.coords, csr.lattice.coords) and np.array_equal(lat.n_vec, csr.lattice.n_vec)
+    assert np.array_equal(lat.rho, csr.lattice.rho) and lat.delta_s == csr.lattice.delta_x
+    x, px, y, py, z, pz = sc["coords"]
+    csr.beam = refstub.FakeBeam(x, px, z, pz, sc["pos"])
+    csr.CSR_scaling = 8.98755e3 * 1e-9
+    csr.formation_length = sc["steps"][-1]["formation_length"]
+    csr.get_CSR_mesh()
+    s = sc["scalars"]
+    xm, zm, xr, zr = O.observation_mesh(x, z, s["slope"], s["sigma_z"], s["mean_z"], 3, 3, 3, 4)
+    assert np.array_equal(xm, csr.CSR_xmesh) and np.array_equal(zm, csr.CSR_zmesh)
+    csr.calculate_2D_CSR()
+    de, kick = O.wake_mesh(xm, zm, O.WakeScalars(nx=30, nz=30, **sc["wake_scalars"]), lat, hs)
+    assert _rel(de, csr.dE_dct.ravel()) < 1e-12 and _rel(kick, csr.x_kick.ravel()) < 1e-12
+
+
+def test_product_lattice_matches_reference(ref, tmp_path):
+    import yaml
+    from pyDFCSR_2D.lattice import Lattice as RefLattice
+    from pydfcsr_b200 import synth
+    from pydfcsr_b200.lattice import Lattice
+    path = str(tmp_path / "lat.yaml")
+    with open(path, "w") as fh:
+        yaml.safe_dump(dict(synth.chicane_lattice_config()), fh, sort_keys=False)
+    a, b = Lattice({"lattice_input_file": path}), RefLattice({"lattice_input_file": path})
+    for k in ("coords", "n_vec", "tau_vec", "rho", "distance", "nsep", "steps_per_element", "steps_record"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert a.delta_x == b.delta_x and a.total_steps == b.total_steps and a.step_size == b.step_size
+    assert np.array_equal(a.CSR_steps_index, b.CSR_steps_index)
