@@ -179,6 +179,19 @@ def oracle_state(wl):
     return xm, zm, sc, lat, hist.stack()
 
 
+def l1_probe():
+    """Measured L1 -> register load bandwidth of this GPU (tools/l1_probe.cu, built by pydfcsr_b200/build.py):
+    the unit that bounds the wake kernel.  None when the probe binary is absent."""
+    exe = os.path.join(ROOT, "pydfcsr_b200", "l1_probe")
+    if not os.path.exists(exe):
+        return None
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout.strip().splitlines()[-1]
+        return json.loads(out)
+    except Exception:
+        return None
+
+
 def samples_per_point(sc):
     return (4 if abs(sc.slope0) <= 1 else 5) * sc.nx * sc.nz
 
@@ -229,7 +242,8 @@ def gpu_arm(args):
     parallel = world > 1
     if args.gpus != world:
         print(f"[bench] --gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun for N>1", file=sys.stderr)
-    csr = CSR2D(_input_dict(wl), parallel=parallel, verbose=False)
+    probe = l1_probe() if int(os.environ.get("RANK", "0")) == 0 else None
+    csr = CSR2D(_input_dict(wl), parallel=parallel, verbose=False, precision=args.precision)
     rank, dev = csr.rank, csr.device
     csr.run(stop_time=wl["position"] - 0.05)                  # builds the 7-slice history on the device
     assert abs(csr.beam.position - wl["position"]) < 1e-9, csr.beam.position
@@ -330,7 +344,8 @@ def gpu_arm(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    k4_bytes = 320.0 * n_in_local          # 5 fields x 8 corners x 8 B per in-grid sample
+    # 5 fields x 8 corners x 8 B per in-grid sample; 4 B in the optional fp32-storage mode
+    k4_bytes = (320.0 if args.precision == "fp64" else 160.0) * n_in_local
     achieved = k4_bytes / (k4_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -357,6 +372,14 @@ def gpu_arm(args):
                              "(stack footprint << bytes), so frac can exceed 1 against the HBM copy peak; the kernel's "
                              "real limiter is the fp64 pipe (see DESIGN.md, profiles/)"},
     }
+    if probe:
+        l1_peak = max(probe["l1_broadcast_gbs"], probe["l1_contiguous_gbs"])
+        line["roofline"]["l1_gather"] = {"achieved": achieved, "peak": l1_peak, "unit": "GB/s", "frac": achieved / l1_peak,
+                                         "how": "peak = 16-byte loads from an L1-resident window, tools/l1_probe.cu, same GPU, "
+                                                "same process start; achieved = same algorithmic bytes as above", "probe": probe}
+    if args.precision != "fp64":
+        line["dtype"] = "f64 math, f32 history storage (optional mode, wakes within 1e-4)"
+        line["config"]["workload"] += "_" + args.precision + "_history"
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         # identical inputs for the checker: export the device history (7 slices) to the host
@@ -409,6 +432,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", choices=["fp64", "fp32"], default="fp64",
+                    help="history storage: fp64 = parity mode (default, the benchmarked configuration); fp32 = optional mode")
     ap.add_argument("--cpu-points-per-core", type=int, default=256, help="mesh points per host core in the cpu_baseline leg")
     ap.add_argument("--ref-points-per-core", type=int, default=256, help="mesh points per host core per step (--impl reference)")
     args = ap.parse_args()

@@ -35,7 +35,8 @@ extern "C" {
 #endif
 
 #define DFCSR_ABI_VERSION 1
-#define DFCSR_VOXEL_DOUBLES 6
+#define DFCSR_VOXEL_DOUBLES 6   /* fp64 voxel: 48 bytes */
+#define DFCSR_VOXEL_FLOATS 8    /* fp32 voxel: 32 bytes {density, density_x, density_z, vx, vx_x, 0, 0, 0} */
 #define DFCSR_LATTICE_DOUBLES 6
 #define DFCSR_STATS_DOUBLES 16
 #define DFCSR_DF_SCALARS 8
@@ -48,6 +49,12 @@ typedef enum dfcsr_status {
     DFCSR_ERR_UNSUPPORTED = -3, /* size outside what the kernels support        */
     DFCSR_ERR_WORKSPACE = -4  /* workspace too small                           */
 } dfcsr_status;
+
+/* storage format of the history ring.  F64 is the parity mode (wakes within 1e-10 of the reference);
+ * F32 is the optional mixed-precision mode of BASELINE.json north_star: the five fields are STORED and
+ * blended in fp32, while geometry, retarded time, cell indices, integrand algebra and the quadrature
+ * stay fp64 (wakes within 1e-4, measured ~1e-7). */
+typedef enum dfcsr_voxel_format { DFCSR_VOXEL_F64 = 0, DFCSR_VOXEL_F32 = 1 } dfcsr_voxel_format;
 
 typedef enum dfcsr_field {
     DFCSR_DENSITY = 0, DFCSR_DENSITY_X = 1, DFCSR_DENSITY_Z = 2, DFCSR_VX = 3, DFCSR_VX_X = 4
@@ -72,12 +79,12 @@ typedef struct dfcsr_axis {
 
 /* device-resident (t', x, z) history published by DF_tracker.build_interpolant (deposit.py:395-426) */
 typedef struct dfcsr_history {
-    const double* d_ring;      /* cap voxel slices                                   */
-    int64_t slice_doubles;     /* X * Z * DFCSR_VOXEL_DOUBLES                        */
+    const void* d_ring;        /* cap voxel slices (doubles or floats, see format)   */
+    int64_t slice_elems;       /* scalars per slice: X * Z * DFCSR_VOXEL_DOUBLES (or _FLOATS) */
     int32_t cap;               /* slots in the ring                                  */
     int32_t head;              /* slot of the oldest slice in the window             */
     int32_t T, X, Z;           /* window depth and slice shape                       */
-    int32_t _pad;
+    int32_t format;            /* dfcsr_voxel_format                                 */
     double min_t, min_x, min_z;      /* deposit.py:416-418 (min_x / min_y / min_z there) */
     double delta_t, delta_x, delta_z;/* deposit.py:419-421                               */
 } dfcsr_history;
@@ -118,7 +125,8 @@ int dfcsr_beam_stats(const double* d_x, const double* d_z, const double* d_pz, i
 /* ---- A1 / K1 particle deposition (deposit.py:42-87, called at deposit.py:172,178) --------------
  * One pass deposits both weights (w = 1 and w = px) with CIC on an (nx, nz) grid whose bin spacing
  * is (end - start) / n.  d_count / d_vxsum (nx*nz doubles each) are zeroed by the call.
- * mode 0 = automatic, 1 = block-private shared-memory tiles, 2 = direct L2 reductions. */
+ * mode 0 = automatic, 1 = block-private shared-memory tile + warp match, 2 = direct L2 reductions,
+ * 3 = block-private tile without the warp match. */
 int dfcsr_deposit_cic(const double* d_x, const double* d_z, const double* d_px, int64_t n,
                       int32_t nx, double x_start, double x_end,
                       int32_t nz, double z_start, double z_end,
@@ -152,11 +160,11 @@ int dfcsr_make_df(const double* d_count, const double* d_vxsum, dfcsr_axis x_axi
  * scalars[4] of dfcsr_make_df, so the host never has to read it back), else fill_vx_x. */
 int dfcsr_history_regrid(const double* d_fields, dfcsr_axis src_x, dfcsr_axis src_z,
                          dfcsr_axis dst_x, dfcsr_axis dst_z, double fill_vx_x, const double* d_fill_vx_x,
-                         double* d_slice, void* stream);
+                         int32_t format, void* d_slice, void* stream);
 
 /* field stack (5, X, Z) <-> voxel slice (X, Z, 6): import/export of oracle histories in tests */
-int dfcsr_history_pack(const double* d_fields, int32_t X, int32_t Z, double* d_slice, void* stream);
-int dfcsr_history_unpack(const double* d_slice, int32_t X, int32_t Z, double* d_fields, void* stream);
+int dfcsr_history_pack(const double* d_fields, int32_t X, int32_t Z, int32_t format, void* d_slice, void* stream);
+int dfcsr_history_unpack(const void* d_slice, int32_t X, int32_t Z, int32_t format, double* d_fields, void* stream);
 
 /* ---- A10-A12 / K4 wake on the observation mesh (CSR.py:397-451, 454-602, 605-782) --------------
  * For k in [0, count): s = t + d_zmesh[first + k], x = d_xmesh[first + k];

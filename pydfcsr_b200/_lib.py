@@ -9,9 +9,11 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdfcsr_b200.so")
+LIB_PATH = os.environ.get("DFCSR_LIB", os.path.join(HERE, "libdfcsr_b200.so"))   # DFCSR_LIB: developer override
 
 VOXEL_DOUBLES = 6
+VOXEL_FLOATS = 8
+VOXEL_F64, VOXEL_F32 = 0, 1
 LATTICE_DOUBLES = 6
 STATS_DOUBLES = 16
 DF_SCALARS = 8
@@ -31,8 +33,8 @@ class Axis(C.Structure):
 
 
 class History(C.Structure):
-    _fields_ = [("d_ring", C.c_void_p), ("slice_doubles", C.c_int64), ("cap", C.c_int32), ("head", C.c_int32),
-                ("T", C.c_int32), ("X", C.c_int32), ("Z", C.c_int32), ("_pad", C.c_int32),
+    _fields_ = [("d_ring", C.c_void_p), ("slice_elems", C.c_int64), ("cap", C.c_int32), ("head", C.c_int32),
+                ("T", C.c_int32), ("X", C.c_int32), ("Z", C.c_int32), ("format", C.c_int32),
                 ("min_t", C.c_double), ("min_x", C.c_double), ("min_z", C.c_double),
                 ("delta_t", C.c_double), ("delta_x", C.c_double), ("delta_z", C.c_double)]
 
@@ -64,9 +66,9 @@ SIGNATURES = {
     "dfcsr_deposit_ngp": (C.c_int, [_P, _P, _L, _I, _D, _D, _I, _D, _D, _P, _P]),
     "dfcsr_make_df_workspace": (_L, [_I, _I]),
     "dfcsr_make_df": (C.c_int, [_P, _P, Axis, Axis, _I, _P, _P, _P, _D, _P, _P, _P, _P]),
-    "dfcsr_history_regrid": (C.c_int, [_P, Axis, Axis, Axis, Axis, _D, _P, _P, _P]),
-    "dfcsr_history_pack": (C.c_int, [_P, _I, _I, _P, _P]),
-    "dfcsr_history_unpack": (C.c_int, [_P, _I, _I, _P, _P]),
+    "dfcsr_history_regrid": (C.c_int, [_P, Axis, Axis, Axis, Axis, _D, _P, _I, _P, _P]),
+    "dfcsr_history_pack": (C.c_int, [_P, _I, _I, _I, _P, _P]),
+    "dfcsr_history_unpack": (C.c_int, [_P, _I, _I, _I, _P, _P]),
     "dfcsr_wake_mesh": (C.c_int, [C.POINTER(History), C.POINTER(Lattice), C.POINTER(WakeParams),
                                   _P, _P, _L, _L, _P, _P, _P, _P]),
     "dfcsr_wake_point_debug": (C.c_int, [C.POINTER(History), C.POINTER(Lattice), C.POINTER(WakeParams),

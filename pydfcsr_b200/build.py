@@ -33,6 +33,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building libdfcsr_b200.so")
     if verbose:
         sys.stderr.write(res.stderr)
+    # measurement helper (not part of the library): L1 load-bandwidth probe used by bench.py
+    probe_src = os.path.join(HERE, "..", "tools", "l1_probe.cu")
+    if os.path.exists(probe_src):
+        subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-o",
+                        os.path.join(HERE, "l1_probe"), probe_src], capture_output=True, text=True)
     return LIB
 
 

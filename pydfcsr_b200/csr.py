@@ -38,7 +38,10 @@ def isotime():
 
 
 class CSR2D:
-    def __init__(self, input_file=None, parallel=False, device=None, verbose=True):
+    def __init__(self, input_file=None, parallel=False, device=None, verbose=True, precision="fp64"):
+        """precision='fp32' selects the optional mixed-precision history (wakes within 1e-4; default is
+        the fp64 parity mode).  Everything else is the reference's signature."""
+        self.precision = precision
         self.timestamp = isotime()
         self.verbose = verbose
         self.parallel = bool(parallel)
@@ -66,7 +69,7 @@ class CSR2D:
         self.input = inp
         self.beam = Beam(inp["input_beam"], device=self.device)
         self.lattice = Lattice(inp["input_lattice"])
-        self.DF_tracker = DF_tracker(inp.get("particle_deposition"), device=self.device)
+        self.DF_tracker = DF_tracker(inp.get("particle_deposition"), device=self.device, precision=self.precision)
         self.integration_params = Integration_params(inp.get("CSR_integration"))
         self.CSR_params = CSR_params(inp.get("CSR_computation"))
 

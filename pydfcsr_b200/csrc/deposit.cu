@@ -6,15 +6,19 @@
 // i = floor(c), S_low = 1-(c-i), and each of the four corner updates guarded separately by
 // 0 <= index < nbins, so particles near the edge deposit partially.
 //
-// Two code paths
-//   private : each CTA owns a full copy of both grids in shared memory (fits for the reference's
-//             hard-coded 100x100 branch, deposit.py:164-167: 2*100*100*8 B = 160 KB of the 227 KB),
-//             lanes that hit the same lower-left cell are combined with a warp match before the
-//             shared-memory atomics, and non-zero cells are flushed with fp64 L2 reductions;
-//   direct  : fp64 reductions (RED.ADD.F64) straight into the L2-resident global grids, for grids
-//             that do not fit in shared memory (YAML grids such as 300x300 or 64x2048).
+// Code paths
+//   tile   : every CTA keeps a private copy of a centred sub-rectangle of BOTH grids in shared memory
+//            (up to 12288 cells = 192 KB: the whole grid for the reference's hard-coded 100x100 branch,
+//            deposit.py:164-167; the central ~+-1.9 sigma, i.e. ~88 % of a Gaussian bunch, for a 300x300
+//            YAML grid).  Updates inside the tile are shared-memory fp64 atomics, optionally after a
+//            warp match that merges lanes hitting the same cell; the few updates outside go straight
+//            to L2 (fp64 RED).  Non-zero tile cells are flushed with fp64 L2 reductions at the end.
+//   direct : fp64 reductions (RED.ADD.F64) into the L2-resident global grids for every update.
 // fp64 atomics make the summation order run-dependent (last-bit differences only).
-// Bound: HBM read of 24 B / particle.
+//
+// Bound: 24 B / particle of HBM reads, but the unit that saturates first is the atomic path: 8 fp64
+// updates per particle at ~1 shared-memory CAS update per clock per SM (shared memory has no native
+// fp64/fp32 add on sm_100a: ATOMS.CAST.SPIN) — see DESIGN.md §4.
 //
 // NGP (nearest grid point) is an extension with no reference counterpart:
 // int64 counts, bit-exact for any order.
@@ -22,9 +26,17 @@
 
 namespace dfcsr {
 
+constexpr int kTileCells = 12288;      // 2 grids x 8 B x 12288 = 192 KB of the 227 KB per CTA
+constexpr int kTileThreads = 1024;
+constexpr long long kParticlesPerCta = 8192;
+
 struct DepGrid {
     int nx, nz;
     double x_start, inv_dx, z_start, inv_dz;
+};
+
+struct Tile {
+    int i0, j0, ni, nj;   // sub-rectangle [i0, i0+ni) x [j0, j0+nj) of the grid
 };
 
 struct CicSample {
@@ -65,18 +77,38 @@ cic_direct_kernel(const double* __restrict__ x, const double* __restrict__ z, co
     }
 }
 
-// Block-private tiles: both grids live in dynamic shared memory.
-__global__ void __launch_bounds__(1024, 1)
-cic_private_kernel(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ px,
-                   long long n, DepGrid g, double* __restrict__ count, double* __restrict__ vxsum) {
+// (A {count, vx} pair update with one 128-bit shared CAS, ATOMS.CAS.128, was measured: the retry loop is
+// 3-4x slower than two ATOMS.CAST.SPIN.64 on the hot central cells, so it is not used.)
+// one corner update: shared-memory tile if the cell is inside it, L2 reduction otherwise
+__device__ __forceinline__ void corner(const DepGrid& g, const Tile& t, double* t_count, double* t_vx,
+                                       double* __restrict__ count, double* __restrict__ vxsum, int i, int j,
+                                       double c, double v) {
+    if (i < 0 || i >= g.nx || j < 0 || j >= g.nz) return;     // the reference's per-corner guards
+    const int ti = i - t.i0, tj = j - t.j0;
+    if (ti >= 0 && ti < t.ni && tj >= 0 && tj < t.nj) {
+        const int o = ti * t.nj + tj;
+        atomicAdd(t_count + o, c);
+        atomicAdd(t_vx + o, v);
+    } else {
+        const long long o = (long long)i * g.nz + j;
+        atomicAdd(count + o, c);
+        atomicAdd(vxsum + o, v);
+    }
+}
+
+template <bool kAggregate>
+__global__ void __launch_bounds__(kTileThreads, 1)
+cic_tile_kernel(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ px,
+                long long n, DepGrid g, Tile t, double* __restrict__ count, double* __restrict__ vxsum) {
     extern __shared__ double tile[];
-    const int cells = g.nx * g.nz;
+    const int cells = t.ni * t.nj;
     double* t_count = tile;
     double* t_vx = tile + cells;
     for (int c = threadIdx.x; c < 2 * cells; c += blockDim.x) tile[c] = 0.0;
     __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long rounds = (n + stride - 1) / stride;   // uniform trip count: the warp match needs all lanes
+    const int lane = threadIdx.x & 31;
     for (long long rnd = 0; rnd < rounds; ++rnd) {
         const long long p = rnd * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
         const bool live = p < n;
@@ -90,46 +122,47 @@ cic_private_kernel(const double* __restrict__ x, const double* __restrict__ z, c
         const double a_hi = 1.0 - s.a_lo, b_hi = 1.0 - s.b_lo;
         double c00 = s.a_lo * s.b_lo, c01 = s.a_lo * b_hi, c10 = a_hi * s.b_lo, c11 = a_hi * b_hi;
         double v00 = w * c00, v01 = w * c01, v10 = w * c10, v11 = w * c11;
-        // warp aggregation: lanes sharing the lower-left cell form a group; the lowest lane of the
-        // group collects the group's eight partial weights and issues the atomics.
-        const int key = live ? (s.i + 2) * (g.nz + 4) + (s.j + 2) : -1 - (int)(threadIdx.x & 31);
-        const unsigned peers = __match_any_sync(0xffffffffu, key);
-        const int leader = __ffs(peers) - 1;
-        const int lane = threadIdx.x & 31;
-        if (peers != (1u << lane)) {
-            // all lanes of a group run the same shuffles (same mask, same trip count); only the
-            // leader keeps the sums
-            unsigned rest = peers & ~(1u << leader);
-            const int steps = __popc(rest);
-            for (int k = 0; k < steps; ++k) {
-                int src = __ffs(rest) - 1;
-                rest &= rest - 1;
-                double t;
-                t = __shfl_sync(peers, c00, src); if (lane == leader) c00 += t;
-                t = __shfl_sync(peers, c01, src); if (lane == leader) c01 += t;
-                t = __shfl_sync(peers, c10, src); if (lane == leader) c10 += t;
-                t = __shfl_sync(peers, c11, src); if (lane == leader) c11 += t;
-                t = __shfl_sync(peers, v00, src); if (lane == leader) v00 += t;
-                t = __shfl_sync(peers, v01, src); if (lane == leader) v01 += t;
-                t = __shfl_sync(peers, v10, src); if (lane == leader) v10 += t;
-                t = __shfl_sync(peers, v11, src); if (lane == leader) v11 += t;
+        bool owner = live;
+        if (kAggregate) {
+            // warp aggregation: lanes sharing the lower-left cell form a group; the lowest lane of the
+            // group collects the group's eight partial weights and issues the atomics.  All lanes of a
+            // group run the same shuffles (same mask, same trip count).
+            const int key = live ? (s.i + 2) * (g.nz + 4) + (s.j + 2) : -1 - lane;
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            const int leader = __ffs(peers) - 1;
+            owner = live && (lane == leader);
+            if (peers != (1u << lane)) {
+                unsigned rest = peers & ~(1u << leader);
+                const int steps = __popc(rest);
+                for (int k = 0; k < steps; ++k) {
+                    int src = __ffs(rest) - 1;
+                    rest &= rest - 1;
+                    double u;
+                    u = __shfl_sync(peers, c00, src); if (lane == leader) c00 += u;
+                    u = __shfl_sync(peers, c01, src); if (lane == leader) c01 += u;
+                    u = __shfl_sync(peers, c10, src); if (lane == leader) c10 += u;
+                    u = __shfl_sync(peers, c11, src); if (lane == leader) c11 += u;
+                    u = __shfl_sync(peers, v00, src); if (lane == leader) v00 += u;
+                    u = __shfl_sync(peers, v01, src); if (lane == leader) v01 += u;
+                    u = __shfl_sync(peers, v10, src); if (lane == leader) v10 += u;
+                    u = __shfl_sync(peers, v11, src); if (lane == leader) v11 += u;
+                }
             }
         }
-        if (live && lane == leader) {
-            const bool i0 = (s.i >= 0) && (s.i < g.nx), i1 = (s.i + 1 >= 0) && (s.i + 1 < g.nx);
-            const bool j0 = (s.j >= 0) && (s.j < g.nz), j1 = (s.j + 1 >= 0) && (s.j + 1 < g.nz);
-            const int o = s.i * g.nz + s.j;
-            if (i0 && j0) { atomicAdd(t_count + o, c00); atomicAdd(t_vx + o, v00); }
-            if (i0 && j1) { atomicAdd(t_count + o + 1, c01); atomicAdd(t_vx + o + 1, v01); }
-            if (i1 && j0) { atomicAdd(t_count + o + g.nz, c10); atomicAdd(t_vx + o + g.nz, v10); }
-            if (i1 && j1) { atomicAdd(t_count + o + g.nz + 1, c11); atomicAdd(t_vx + o + g.nz + 1, v11); }
+        if (owner) {
+            corner(g, t, t_count, t_vx, count, vxsum, s.i, s.j, c00, v00);
+            corner(g, t, t_count, t_vx, count, vxsum, s.i, s.j + 1, c01, v01);
+            corner(g, t, t_count, t_vx, count, vxsum, s.i + 1, s.j, c10, v10);
+            corner(g, t, t_count, t_vx, count, vxsum, s.i + 1, s.j + 1, c11, v11);
         }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < cells; c += blockDim.x) {
+        const int ti = c / t.nj, tj = c - ti * t.nj;
+        const long long o = (long long)(t.i0 + ti) * g.nz + (t.j0 + tj);
         double a = t_count[c], b = t_vx[c];
-        if (a != 0.0) atomicAdd(count + c, a);
-        if (b != 0.0) atomicAdd(vxsum + c, b);
+        if (a != 0.0) atomicAdd(count + o, a);
+        if (b != 0.0) atomicAdd(vxsum + o, b);
     }
 }
 
@@ -156,6 +189,24 @@ static DepGrid make_grid(int nx, double xs, double xe, int nz, double zs, double
     return g;
 }
 
+// centred sub-rectangle with the grid's aspect ratio and at most kTileCells cells
+static Tile make_tile(int nx, int nz) {
+    Tile t;
+    if ((long long)nx * nz <= kTileCells) {
+        t.i0 = 0; t.j0 = 0; t.ni = nx; t.nj = nz;
+        return t;
+    }
+    double f = sqrt((double)kTileCells / ((double)nx * (double)nz));
+    int ni = (int)(nx * f);
+    ni = ni < 1 ? 1 : (ni > nx ? nx : ni);
+    int nj = kTileCells / ni;
+    nj = nj > nz ? nz : nj;
+    t.ni = ni; t.nj = nj;
+    t.i0 = (nx - ni) / 2;
+    t.j0 = (nz - nj) / 2;
+    return t;
+}
+
 }  // namespace dfcsr
 
 using namespace dfcsr;
@@ -166,33 +217,34 @@ extern "C" int dfcsr_deposit_cic(const double* d_x, const double* d_z, const dou
     DFCSR_REQUIRE(d_count && d_vxsum && (n == 0 || (d_x && d_z && d_px)), "null pointer");
     DFCSR_REQUIRE(nx >= 1 && nz >= 1 && n >= 0, "bad sizes");
     DFCSR_REQUIRE((long long)nx * nz < (1LL << 30), "grid too large");
+    DFCSR_REQUIRE(mode >= 0 && mode <= 3, "mode must be 0 (auto), 1 (tile + warp match), 2 (direct) or 3 (tile)");
     cudaStream_t st = as_stream(stream);
     const size_t cells = (size_t)nx * nz;
     DFCSR_CUDA_OK(cudaMemsetAsync(d_count, 0, cells * sizeof(double), st));
     DFCSR_CUDA_OK(cudaMemsetAsync(d_vxsum, 0, cells * sizeof(double), st));
     if (n == 0) return DFCSR_OK;
     DepGrid g = make_grid(nx, x_start, x_end, nz, z_start, z_end);
-    const size_t smem = 2 * cells * sizeof(double);
-    const bool fits = smem <= 200 * 1024;
-    if (mode == 0) mode = (fits && n >= (4LL << 20)) ? 1 : 2;
-    if (mode == 1) {
-        if (!fits) {
-            set_error("dfcsr_deposit_cic: %dx%d grid does not fit the shared-memory tile path", nx, nz);
-            return DFCSR_ERR_UNSUPPORTED;
-        }
-        DFCSR_CUDA_OK(cudaFuncSetAttribute(cic_private_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        long long want = (n + 1024LL * 32 - 1) / (1024LL * 32);
-        unsigned blocks = (unsigned)(want < 148 ? (want < 1 ? 1 : want) : 148);
-        cic_private_kernel<<<blocks, 1024, smem, st>>>(d_x, d_z, d_px, n, g, d_count, d_vxsum);
-    count_launch(1);
-    } else if (mode == 2) {
+    if (mode == 0) mode = (n >= 65536) ? 3 : 2;
+    if (mode == 2) {
         long long want = (n + 255) / 256;
         unsigned blocks = (unsigned)(want < 148LL * 8 ? want : 148LL * 8);
         cic_direct_kernel<<<blocks, 256, 0, st>>>(d_x, d_z, d_px, n, g, d_count, d_vxsum);
-    count_launch(1);
     } else {
-        DFCSR_REQUIRE(false, "mode must be 0, 1 or 2");
+        Tile t = make_tile(nx, nz);
+        const size_t smem = (size_t)2 * t.ni * t.nj * sizeof(double);
+        long long want = (n + kParticlesPerCta - 1) / kParticlesPerCta;
+        unsigned blocks = (unsigned)(want < 148 ? (want < 1 ? 1 : want) : 148);
+#define DFCSR_LAUNCH_TILE(AGG)                                                                               \
+    do {                                                                                                     \
+        DFCSR_CUDA_OK(cudaFuncSetAttribute(cic_tile_kernel<AGG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           (int)smem));                                                      \
+        cic_tile_kernel<AGG><<<blocks, kTileThreads, smem, st>>>(d_x, d_z, d_px, n, g, t, d_count, d_vxsum);  \
+    } while (0)
+        if (mode == 1) DFCSR_LAUNCH_TILE(true);
+        else DFCSR_LAUNCH_TILE(false);
+#undef DFCSR_LAUNCH_TILE
     }
+    count_launch(1);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;
 }

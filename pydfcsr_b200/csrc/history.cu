@@ -20,7 +20,7 @@
 namespace dfcsr {
 
 constexpr int kRegridCols = 128;   // threads per block = columns (z) per tile
-constexpr int kRegridRows = 16;    // rows (x) per tile
+constexpr int kRegridRows = 4;     // rows (x) per tile
 
 struct AxisCell {
     int i;
@@ -48,9 +48,38 @@ __device__ inline AxisCell locate(const Axis& g, double q) {
     return c;
 }
 
+// one voxel to a slice: 48-byte fp64 record or 32-byte fp32 record
+template <bool kF32>
+__device__ __forceinline__ void store_voxel(void* slice, size_t cell, const double (&v)[5]) {
+    if (kF32) {
+        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(slice) + cell * DFCSR_VOXEL_FLOATS);
+        dst[0] = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+        dst[1] = make_float4((float)v[4], 0.f, 0.f, 0.f);
+    } else {
+        double2* dst = reinterpret_cast<double2*>(reinterpret_cast<double*>(slice) + cell * DFCSR_VOXEL_DOUBLES);
+        dst[0] = make_double2(v[0], v[1]);
+        dst[1] = make_double2(v[2], v[3]);
+        dst[2] = make_double2(v[4], 0.0);
+    }
+}
+
+template <bool kF32>
+__device__ __forceinline__ void load_voxel(const void* slice, size_t cell, double (&v)[5]) {
+    if (kF32) {
+        const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(slice) + cell * DFCSR_VOXEL_FLOATS);
+        float4 a = src[0], b = src[1];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x;
+    } else {
+        const double2* src = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(slice) + cell * DFCSR_VOXEL_DOUBLES);
+        double2 a = src[0], b = src[1], d = src[2];
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = d.x;
+    }
+}
+
+template <bool kF32>
 __global__ void __launch_bounds__(kRegridCols)
 regrid_kernel(const double* __restrict__ src, Axis sx, Axis sz, Axis dx, Axis dz, double fill_vx_x,
-              const double* __restrict__ fill_ptr, double* __restrict__ slice) {
+              const double* __restrict__ fill_ptr, void* __restrict__ slice) {
     __shared__ AxisCell rows[kRegridRows];
     if (fill_ptr) fill_vx_x = __ldg(fill_ptr);
     const int col = blockIdx.x * kRegridCols + threadIdx.x;
@@ -67,7 +96,7 @@ regrid_kernel(const double* __restrict__ src, Axis sx, Axis sz, Axis dx, Axis dz
     const int rmax = min(kRegridRows, dx.n - row0);
     for (int r = 0; r < rmax; ++r) {
         const AxisCell cx = rows[r];
-        double out[DFCSR_VOXEL_DOUBLES];
+        double out[5];
         if (cx.outside || cz.outside) {
             out[0] = out[1] = out[2] = out[3] = 0.0;
             out[4] = fill_vx_x;
@@ -85,34 +114,29 @@ regrid_kernel(const double* __restrict__ src, Axis sx, Axis sz, Axis dx, Axis dz
                 out[f] = v;
             }
         }
-        out[5] = 0.0;
-        double2* dst = reinterpret_cast<double2*>(slice + ((size_t)(row0 + r) * dz.n + col) * DFCSR_VOXEL_DOUBLES);
-        dst[0] = make_double2(out[0], out[1]);
-        dst[1] = make_double2(out[2], out[3]);
-        dst[2] = make_double2(out[4], out[5]);
+        store_voxel<kF32>(slice, (size_t)(row0 + r) * dz.n + col, out);
     }
 }
 
-__global__ void pack_kernel(const double* __restrict__ fields, long long cells, double* __restrict__ slice) {
+template <bool kF32>
+__global__ void pack_kernel(const double* __restrict__ fields, long long cells, void* __restrict__ slice) {
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < cells;
          c += (long long)gridDim.x * blockDim.x) {
-        double2* dst = reinterpret_cast<double2*>(slice + c * DFCSR_VOXEL_DOUBLES);
-        dst[0] = make_double2(fields[c], fields[cells + c]);
-        dst[1] = make_double2(fields[2 * cells + c], fields[3 * cells + c]);
-        dst[2] = make_double2(fields[4 * cells + c], 0.0);
+        double v[5];
+#pragma unroll
+        for (int f = 0; f < 5; ++f) v[f] = fields[f * cells + c];
+        store_voxel<kF32>(slice, (size_t)c, v);
     }
 }
 
-__global__ void unpack_kernel(const double* __restrict__ slice, long long cells, double* __restrict__ fields) {
+template <bool kF32>
+__global__ void unpack_kernel(const void* __restrict__ slice, long long cells, double* __restrict__ fields) {
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < cells;
          c += (long long)gridDim.x * blockDim.x) {
-        const double2* src = reinterpret_cast<const double2*>(slice + c * DFCSR_VOXEL_DOUBLES);
-        double2 a = src[0], b = src[1], d = src[2];
-        fields[c] = a.x;
-        fields[cells + c] = a.y;
-        fields[2 * cells + c] = b.x;
-        fields[3 * cells + c] = b.y;
-        fields[4 * cells + c] = d.x;
+        double v[5];
+        load_voxel<kF32>(slice, (size_t)c, v);
+#pragma unroll
+        for (int f = 0; f < 5; ++f) fields[f * cells + c] = v[f];
     }
 }
 
@@ -128,32 +152,40 @@ using namespace dfcsr;
 
 extern "C" int dfcsr_history_regrid(const double* d_fields, dfcsr_axis src_x, dfcsr_axis src_z,
                                     dfcsr_axis dst_x, dfcsr_axis dst_z, double fill_vx_x,
-                                    const double* d_fill_vx_x, double* d_slice, void* stream) {
+                                    const double* d_fill_vx_x, int32_t format, void* d_slice, void* stream) {
     DFCSR_REQUIRE(d_fields && d_slice, "null pointer");
     DFCSR_REQUIRE(src_x.n >= 2 && src_z.n >= 2 && dst_x.n >= 1 && dst_z.n >= 1, "axes too short");
     Axis sx = make_axis(src_x.start, src_x.stop, src_x.n), sz = make_axis(src_z.start, src_z.stop, src_z.n);
     Axis dx = make_axis(dst_x.start, dst_x.stop, dst_x.n), dz = make_axis(dst_z.start, dst_z.stop, dst_z.n);
     dim3 grid((dz.n + kRegridCols - 1) / kRegridCols, (dx.n + kRegridRows - 1) / kRegridRows);
     DFCSR_REQUIRE(grid.y <= 65535, "destination grid too tall");
-    regrid_kernel<<<grid, kRegridCols, 0, as_stream(stream)>>>(d_fields, sx, sz, dx, dz, fill_vx_x, d_fill_vx_x, d_slice);
+    DFCSR_REQUIRE(format == DFCSR_VOXEL_F64 || format == DFCSR_VOXEL_F32, "unknown voxel format");
+    if (format == DFCSR_VOXEL_F32)
+        regrid_kernel<true><<<grid, kRegridCols, 0, as_stream(stream)>>>(d_fields, sx, sz, dx, dz, fill_vx_x, d_fill_vx_x, d_slice);
+    else
+        regrid_kernel<false><<<grid, kRegridCols, 0, as_stream(stream)>>>(d_fields, sx, sz, dx, dz, fill_vx_x, d_fill_vx_x, d_slice);
     count_launch(1);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;
 }
 
-extern "C" int dfcsr_history_pack(const double* d_fields, int32_t X, int32_t Z, double* d_slice, void* stream) {
+extern "C" int dfcsr_history_pack(const double* d_fields, int32_t X, int32_t Z, int32_t format, void* d_slice, void* stream) {
     DFCSR_REQUIRE(d_fields && d_slice && X > 0 && Z > 0, "bad argument");
+    DFCSR_REQUIRE(format == DFCSR_VOXEL_F64 || format == DFCSR_VOXEL_F32, "unknown voxel format");
     long long cells = (long long)X * Z;
-    pack_kernel<<<blocks_for(cells, 256), 256, 0, as_stream(stream)>>>(d_fields, cells, d_slice);
+    if (format == DFCSR_VOXEL_F32) pack_kernel<true><<<blocks_for(cells, 256), 256, 0, as_stream(stream)>>>(d_fields, cells, d_slice);
+    else pack_kernel<false><<<blocks_for(cells, 256), 256, 0, as_stream(stream)>>>(d_fields, cells, d_slice);
     count_launch(1);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;
 }
 
-extern "C" int dfcsr_history_unpack(const double* d_slice, int32_t X, int32_t Z, double* d_fields, void* stream) {
+extern "C" int dfcsr_history_unpack(const void* d_slice, int32_t X, int32_t Z, int32_t format, double* d_fields, void* stream) {
     DFCSR_REQUIRE(d_fields && d_slice && X > 0 && Z > 0, "bad argument");
+    DFCSR_REQUIRE(format == DFCSR_VOXEL_F64 || format == DFCSR_VOXEL_F32, "unknown voxel format");
     long long cells = (long long)X * Z;
-    unpack_kernel<<<blocks_for(cells, 256), 256, 0, as_stream(stream)>>>(d_slice, cells, d_fields);
+    if (format == DFCSR_VOXEL_F32) unpack_kernel<true><<<blocks_for(cells, 256), 256, 0, as_stream(stream)>>>(d_slice, cells, d_fields);
+    else unpack_kernel<false><<<blocks_for(cells, 256), 256, 0, as_stream(stream)>>>(d_slice, cells, d_fields);
     count_launch(1);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;

@@ -40,7 +40,12 @@ class _Record:
 
 
 class DF_tracker:
-    def __init__(self, input_dic=None, device=None, deposit_mode=0):
+    def __init__(self, input_dic=None, device=None, deposit_mode=0, precision="fp64"):
+        """precision: storage format of the history ring — 'fp64' (parity mode, default) or 'fp32'
+        (optional mixed-precision mode: fields stored/blended in fp32, everything else fp64)."""
+        if precision not in ("fp64", "fp32"):
+            raise ValueError("precision must be 'fp64' or 'fp32'")
+        self.precision = precision
         self.configure_params(**(input_dic or {}))
         self.device = torch.device(device if device is not None else "cuda")
         self.deposit_mode = deposit_mode
@@ -175,7 +180,7 @@ class DF_tracker:
         if ring is None or ring.shape[1] != X or ring.shape[2] != Z or ring.shape[0] < need:
             cap = max(16, 1 << (max(need, 1) * 2 - 1).bit_length())
             self._ring = None          # release the old ring before allocating the new one
-            self._ring = torch.empty((cap, X, Z, _lib.VOXEL_DOUBLES), dtype=torch.float64, device=self.device)
+            self._ring = ops.new_slices((cap, X, Z), self.precision, self.device)
             self._head = 0
             return True
         return False
@@ -184,7 +189,7 @@ class DF_tracker:
         """Ring full on a non-rebuild push: double the capacity, keep the window order."""
         old, T = self._ring, len(self.time_interp) - 1
         cap = old.shape[0] * 2
-        new = torch.empty((cap,) + tuple(old.shape[1:]), dtype=torch.float64, device=self.device)
+        new = torch.empty((cap,) + tuple(old.shape[1:]), dtype=old.dtype, device=self.device)
         idx = (torch.arange(T, device=self.device) + self._head) % old.shape[0]
         new[:T] = old[idx]
         self._ring, self._head = new, 0

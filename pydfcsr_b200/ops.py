@@ -127,26 +127,45 @@ def make_df(count, vxsum, x_axis: Axis, z_axis: Axis, window: int, order: int, v
 # ---------------------------------------------------------------------------------------------
 # K3 history
 # ---------------------------------------------------------------------------------------------
+def voxel_format(t: torch.Tensor) -> int:
+    """dfcsr_voxel_format of a slice/ring tensor: fp64 voxels are (.., 6) doubles, fp32 voxels (.., 8) floats."""
+    if t.dtype == torch.float64 and t.shape[-1] == _lib.VOXEL_DOUBLES:
+        return _lib.VOXEL_F64
+    if t.dtype == torch.float32 and t.shape[-1] == _lib.VOXEL_FLOATS:
+        return _lib.VOXEL_F32
+    raise _lib.DfcsrError(f"not a voxel tensor: dtype {t.dtype}, last dimension {t.shape[-1]}")
+
+
+def new_slices(shape, precision, device) -> torch.Tensor:
+    """Allocate voxel storage: shape + (6,) float64 for 'fp64', shape + (8,) float32 for 'fp32'."""
+    if precision == "fp64":
+        return torch.empty(tuple(shape) + (_lib.VOXEL_DOUBLES,), dtype=torch.float64, device=device)
+    if precision == "fp32":
+        return torch.empty(tuple(shape) + (_lib.VOXEL_FLOATS,), dtype=torch.float32, device=device)
+    raise ValueError("precision must be 'fp64' or 'fp32'")
+
+
 def history_regrid(fields, src_x: Axis, src_z: Axis, dst_x: Axis, dst_z: Axis, fill_vx_x, slice_out):
     """fill_vx_x: host float, or a 1-element CUDA tensor (read on the device, no host sync)."""
     dev_fill = fill_vx_x if isinstance(fill_vx_x, torch.Tensor) else None
     check(lib.dfcsr_history_regrid(_ptr(fields), src_x, src_z, dst_x, dst_z,
                                    0.0 if dev_fill is not None else float(fill_vx_x), _ptr(dev_fill),
-                                   _ptr(slice_out), _stream()), "dfcsr_history_regrid")
+                                   voxel_format(slice_out), _ptr(slice_out), _stream()), "dfcsr_history_regrid")
     return slice_out
 
 
-def history_pack(fields, slice_out=None):
+def history_pack(fields, slice_out=None, precision="fp64"):
     _, X, Z = fields.shape
     if slice_out is None:
-        slice_out = torch.empty((X, Z, _lib.VOXEL_DOUBLES), dtype=F64, device=fields.device)
-    check(lib.dfcsr_history_pack(_ptr(_f64(fields, "fields")), X, Z, _ptr(slice_out), _stream()), "dfcsr_history_pack")
+        slice_out = new_slices((X, Z), precision, fields.device)
+    check(lib.dfcsr_history_pack(_ptr(_f64(fields, "fields")), X, Z, voxel_format(slice_out), _ptr(slice_out), _stream()),
+          "dfcsr_history_pack")
     return slice_out
 
 
 def history_unpack(slice_in, X, Z):
     out = torch.empty((5, X, Z), dtype=F64, device=slice_in.device)
-    check(lib.dfcsr_history_unpack(_ptr(slice_in), X, Z, _ptr(out), _stream()), "dfcsr_history_unpack")
+    check(lib.dfcsr_history_unpack(_ptr(slice_in), X, Z, voxel_format(slice_in), _ptr(out), _stream()), "dfcsr_history_unpack")
     return out
 
 
@@ -178,8 +197,9 @@ class DeviceLattice:
 
 @dataclass
 class DeviceHistory:
-    """Device-resident (t', x, z) history ring of 48-byte voxels."""
-    ring: torch.Tensor        # (cap, X, Z, 6)
+    """Device-resident (t', x, z) history ring: 48-byte fp64 voxels, or 32-byte fp32 voxels in the
+    optional mixed-precision mode."""
+    ring: torch.Tensor        # (cap, X, Z, 6) float64 or (cap, X, Z, 8) float32
     head: int
     T: int
     min_t: float
@@ -190,16 +210,17 @@ class DeviceHistory:
     delta_z: float
 
     def view(self) -> _lib.History:
-        cap, X, Z, _ = self.ring.shape
-        return _lib.History(self.ring.data_ptr(), X * Z * _lib.VOXEL_DOUBLES, cap, self.head, self.T, X, Z, 0,
+        cap, X, Z, elems = self.ring.shape
+        return _lib.History(self.ring.data_ptr(), X * Z * elems, cap, self.head, self.T, X, Z, voxel_format(self.ring),
                             self.min_t, self.min_x, self.min_z, self.delta_t, self.delta_x, self.delta_z)
 
     @classmethod
-    def from_stacks(cls, stacks, min_t, min_x, min_z, delta_t, delta_x, delta_z, device, cap=None, head=0):
+    def from_stacks(cls, stacks, min_t, min_x, min_z, delta_t, delta_x, delta_z, device, cap=None, head=0,
+                    precision="fp64"):
         """Import five host (T, X, Z) arrays in dfcsr_field order (oracle / golden histories)."""
         T, X, Z = stacks[0].shape
         cap = cap or T
-        ring = torch.zeros((cap, X, Z, _lib.VOXEL_DOUBLES), dtype=F64, device=device)
+        ring = new_slices((cap, X, Z), precision, device).zero_()
         for k in range(T):
             fields = torch.from_numpy(np.ascontiguousarray(np.stack([s[k] for s in stacks]))).to(device)
             history_pack(fields, ring[(head + k) % cap])

@@ -36,15 +36,14 @@ def test_deposit_conservation_and_linearity_at_scale(n, shape):
     z = torch.randn(n, generator=g, device="cuda", dtype=torch.float64) * 2.0e-4
     px = torch.randn(n, generator=g, device="cuda", dtype=torch.float64) * 4.0e-6
     nx, nz = shape
-    lim_x, lim_z = float(x.abs().max()) * 1.01, float(z.abs().max()) * 1.01
+    lim_x, lim_z = float(x.abs().max()) * 1.08, float(z.abs().max()) * 1.08   # > one cell of margin
     args = (nx, -lim_x, lim_x, nz, -lim_z, lim_z)
-    fits = 2 * nx * nz * 8 <= 200 * 1024
     c2, v2 = (t.clone() for t in ops.deposit_cic(x, z, px, *args, mode=2))
     assert abs(float(c2.sum()) - n) <= 1e-9 * n
     assert abs(float(v2.sum()) - float(px.sum())) <= 1e-9 * float(px.abs().sum())
     assert float(c2.min()) >= 0.0
-    if fits:
-        c1, v1 = ops.deposit_cic(x, z, px, *args, mode=1)
+    for mode in (1, 3):          # shared-memory tile paths (the 64x512 grid only partly fits the tile)
+        c1, v1 = ops.deposit_cic(x, z, px, *args, mode=mode)
         assert float((c1 - c2).abs().max()) <= 1e-10 * float(c2.max())
         assert float((v1 - v2).abs().max()) <= 1e-10 * float(v2.abs().max())
     h = n // 2
