@@ -27,7 +27,9 @@ namespace cg = cooperative_groups;
 
 namespace dfcsr {
 
-constexpr int kDfCtas = 8;
+constexpr int kDfCtas = 8;        // CTAs of the cluster launch (grids up to kClusterCells cells)
+constexpr int kDfMaxCtas = 64;    // CTAs of the cooperative launch used for larger grids
+constexpr int kClusterCells = 16384;
 constexpr int kDfThreads = 512;
 constexpr int kMaxWindow = 33;
 constexpr int kMaxHalf = kMaxWindow / 2;
@@ -41,7 +43,7 @@ struct DfOps {   // device copy of the Savitzky-Golay operators
 
 struct DfWorkspace {
     DfOps ops;
-    double partial[8][kDfCtas][kPartials];
+    double partial[8][kDfMaxCtas][kPartials];
     // followed by 6 scratch planes of nx*nz doubles
 };
 
@@ -132,21 +134,27 @@ __device__ __forceinline__ void cta_reduce(double (&v)[NV], const bool (&is_max)
 
 __device__ __forceinline__ double combine(double (*p)[kPartials], int slot, bool is_max) {
     double s = ((volatile double*)&p[0][slot])[0];
-    for (int c = 1; c < kDfCtas; ++c) {
+    for (int c = 1; c < (int)gridDim.x; ++c) {
         double t = ((volatile double*)&p[c][slot])[0];
         s = is_max ? fmax(s, t) : s + t;
     }
     return s;
 }
 
-__global__ void __cluster_dims__(kDfCtas, 1, 1) __launch_bounds__(kDfThreads, 1)
-make_df_kernel(DfParams P) {
-    cg::cluster_group cluster = cg::this_cluster();
+struct ClusterSync {   // 8 CTAs on 8 SMs of one GPC: hardware cluster barrier (release/acquire at cluster scope)
+    __device__ __forceinline__ void sync() { cg::this_cluster().sync(); }
+};
+struct GridSync {      // cooperative launch: grid-wide barrier for grids too large for one cluster
+    __device__ __forceinline__ void sync() { cg::this_grid().sync(); }
+};
+
+template <typename Sync>
+__device__ __forceinline__ void make_df_body(const DfParams& P, Sync cluster) {
     const int cta = blockIdx.x;
     const int nx = P.ax.n, nz = P.az.n;
     const int cells = nx * nz;
     const int tid = cta * kDfThreads + threadIdx.x;
-    const int nthreads = kDfCtas * kDfThreads;
+    const int nthreads = (int)gridDim.x * kDfThreads;
     const DfOps& ops = P.ws->ops;
     const int window = P.window;
     double* T0 = P.scratch;
@@ -277,6 +285,12 @@ make_df_kernel(DfParams P) {
     }
 }
 
+__global__ void __cluster_dims__(kDfCtas, 1, 1) __launch_bounds__(kDfThreads, 1) make_df_kernel(DfParams P) {
+    make_df_body(P, ClusterSync());
+}
+
+__global__ void __launch_bounds__(kDfThreads, 1) make_df_kernel_grid(DfParams P) { make_df_body(P, GridSync()); }
+
 }  // namespace dfcsr
 
 using namespace dfcsr;
@@ -319,7 +333,15 @@ extern "C" int dfcsr_make_df(const double* d_count, const double* d_vxsum, dfcsr
     P.scalars = d_scalars;
     P.ws = ws;
     P.scratch = reinterpret_cast<double*>(reinterpret_cast<char*>(d_workspace) + sizeof(DfWorkspace));
-    make_df_kernel<<<kDfCtas, kDfThreads, 0, st>>>(P);
+    const long long cells = (long long)x_axis.n * z_axis.n;
+    if (cells <= kClusterCells) {
+        make_df_kernel<<<kDfCtas, kDfThreads, 0, st>>>(P);
+    } else {
+        long long want = (cells + 2047) / 2048;
+        int ctas = (int)(want < kDfCtas ? kDfCtas : (want > kDfMaxCtas ? kDfMaxCtas : want));
+        void* args[] = {&P};
+        DFCSR_CUDA_OK(cudaLaunchCooperativeKernel((const void*)make_df_kernel_grid, dim3(ctas), dim3(kDfThreads), args, 0, st));
+    }
     count_launch(1);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;

@@ -122,10 +122,14 @@ print("ok", rank)
 
 
 def test_all_gather_blocks_world2_gloo(tmp_path):
+    import socket
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
+    with socket.socket() as sock:                 # a free rendezvous port (fixed ports collide between runs)
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29631", str(script), ROOT]
+           "--master-port", str(port), str(script), ROOT]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "ok 0" in out.stdout and "ok 1" in out.stdout

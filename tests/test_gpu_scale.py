@@ -163,9 +163,13 @@ def test_two_rank_nccl_pipeline():
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    import socket
     script = os.path.join(ROOT, "tests", "nccl_worker.py")
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29641", script]
+           "--master-port", str(port), script]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "nccl ok 0" in out.stdout and "nccl ok 1" in out.stdout

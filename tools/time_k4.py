@@ -12,7 +12,10 @@ from pydfcsr_b200 import CSR2D  # noqa: E402
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 wl = bench.WORKLOAD
-csr = CSR2D(bench._input_dict(wl), parallel=False, verbose=False, precision=os.environ.get('DFCSR_PRECISION', 'fp64'))
+inp = bench._input_dict(wl)
+if os.environ.get('DFCSR_TILT'):
+    inp['input_beam']['tilt'] = float(os.environ['DFCSR_TILT'])
+csr = CSR2D(inp, parallel=False, verbose=False, precision=os.environ.get('DFCSR_PRECISION', 'fp64'))
 csr.run(stop_time=wl["position"] - 0.05)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=csr.device)
 for _ in range(3):
