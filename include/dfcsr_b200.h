@@ -116,8 +116,9 @@ const char* dfcsr_last_error(void);
 int64_t dfcsr_launch_count(void);
 
 /* ---- A14 beam scalars (beams.py:88-98,137-156,201-215; deposit.py:147-159) --------------------
- * Three reduction passes over (x, z[, pz]); results land in d_stats[DFCSR_STATS_DOUBLES].
- * d_workspace needs dfcsr_beam_stats_workspace() bytes.  d_pz may be NULL. */
+ * Two reduction passes over (x, z[, pz]); results land in d_stats[DFCSR_STATS_DOUBLES].
+ * d_workspace needs dfcsr_beam_stats_workspace() bytes, ZERO-INITIALISED once by the caller (the
+ * calls leave it reusable).  d_pz may be NULL. */
 int64_t dfcsr_beam_stats_workspace(void);
 int dfcsr_beam_stats(const double* d_x, const double* d_z, const double* d_pz, int64_t n,
                      double* d_stats, void* d_workspace, void* stream);
@@ -140,8 +141,9 @@ int dfcsr_deposit_ngp(const double* d_x, const double* d_z, int64_t n,
                       int64_t* d_count, void* stream);
 
 /* ---- A2-A4 / K2 density functions (deposit.py:183-235) -----------------------------------------
- * count / vxsum -> the five smoothed fields.  Savitzky-Golay operators for (window, order) are
- * host-computed: h_taps[window], h_edge_lo[half*window], h_edge_hi[half*window] (half = window/2).
+ * count / vxsum -> the five smoothed fields.  The Savitzky-Golay operators for (window, order) are
+ * computed once on the host in fp64 and kept on the device by the caller: d_taps[window],
+ * d_edge_lo[half*window], d_edge_hi[half*window] (half = window/2; scipy's mode='interp' edge fit).
  * d_fields: field stack (5, nx, nz).  d_scalars[DFCSR_DF_SCALARS] receives
  *   [0] max(count)  [1] threshold  [2] trapz normalisation  [3] max(density)
  *   [4] mean(vx_x) after the mask fill (= fill value used by the re-gridding, deposit.py:332)
@@ -149,7 +151,7 @@ int dfcsr_deposit_ngp(const double* d_x, const double* d_z, int64_t n,
  * d_workspace needs dfcsr_make_df_workspace(nx, nz) bytes. */
 int64_t dfcsr_make_df_workspace(int32_t nx, int32_t nz);
 int dfcsr_make_df(const double* d_count, const double* d_vxsum, dfcsr_axis x_axis, dfcsr_axis z_axis,
-                  int32_t window, const double* h_taps, const double* h_edge_lo, const double* h_edge_hi,
+                  int32_t window, const double* d_taps, const double* d_edge_lo, const double* d_edge_hi,
                   double velocity_threshold, double* d_fields, double* d_scalars,
                   void* d_workspace, void* stream);
 
@@ -174,6 +176,15 @@ int dfcsr_history_unpack(const void* d_slice, int32_t X, int32_t Z, int32_t form
 int dfcsr_wake_mesh(const dfcsr_history* hist, const dfcsr_lattice* lat, const dfcsr_wake_params* wp,
                     const double* d_xmesh, const double* d_zmesh, int64_t first, int64_t count,
                     double* d_dE, double* d_kick, unsigned long long* d_counters, void* stream);
+
+/* Same, with the observation mesh generated on the device exactly as get_CSR_mesh builds it
+ * (CSR.py:380-389): point k = (ix, iz) = divmod(k, z_axis.n); z = linspace node iz of z_axis
+ * (CSR_zrange); x = linspace node ix of x_axis (CSR_xrange_transformed) + (slope*z + intercept).
+ * No mesh arrays have to be built or uploaded per step. */
+int dfcsr_wake_grid(const dfcsr_history* hist, const dfcsr_lattice* lat, const dfcsr_wake_params* wp,
+                    dfcsr_axis x_axis, dfcsr_axis z_axis, double slope, double intercept,
+                    int64_t first, int64_t count, double* d_dE, double* d_kick,
+                    unsigned long long* d_counters, void* stream);
 
 /* get_CSR_wake(s, x, debug=True) (CSR.py:571-572, 599-600): integrands of one point.
  * d_iz / d_ix receive the regions back to back, each (n_x, n_s) row-major like the reference's

@@ -71,6 +71,8 @@ SIGNATURES = {
     "dfcsr_history_unpack": (C.c_int, [_P, _I, _I, _I, _P, _P]),
     "dfcsr_wake_mesh": (C.c_int, [C.POINTER(History), C.POINTER(Lattice), C.POINTER(WakeParams),
                                   _P, _P, _L, _L, _P, _P, _P, _P]),
+    "dfcsr_wake_grid": (C.c_int, [C.POINTER(History), C.POINTER(Lattice), C.POINTER(WakeParams), Axis, Axis, _D, _D,
+                                  _L, _L, _P, _P, _P, _P]),
     "dfcsr_wake_point_debug": (C.c_int, [C.POINTER(History), C.POINTER(Lattice), C.POINTER(WakeParams),
                                          _D, _D, _P, _P, _L, _P, _P, _P]),
     "dfcsr_apply_kick": (C.c_int, [_P, _P, _P, _P, _L, _D, _D, _P, _P, Axis, Axis, _D, _D, _I, _P]),

@@ -26,6 +26,7 @@ import torch
 
 from . import distributed as dist_utils
 from . import ops, tracking
+from ._lib import Axis
 from .beams import Beam
 from .deposit import DF_tracker
 from .lattice import Lattice
@@ -254,19 +255,28 @@ class CSR2D:
 
     # ------------------------------------------------------------------------------- mesh + wake
     def get_CSR_mesh(self):
-        """CSR.py:361-394.  The O(Np) statistics of x_transform come from the device reductions;
-        the mesh itself (<= 32768 points) is built on the host exactly as the reference does."""
+        """CSR.py:361-394.  Only the two axes (xbins + zbins numbers) are built on the host; the N mesh
+        points themselves are generated inside the wake kernel from the axes and the chirp line
+        (`dfcsr_wake_grid`), so nothing O(N) is built or uploaded per step.  `CSR_xmesh` / `CSR_zmesh`
+        remain available as lazily evaluated host arrays."""
         b, p = self.beam, self.CSR_params
-        slope = b._slope
         sig_x, mean_x = b.sigma_x_transform, b.mean_x_transform
-        zrange = np.linspace(b.mean_z - p.zlim * b.sigma_z, b.mean_z + p.zlim * b.sigma_z, p.zbins)
-        xrange = np.linspace(mean_x - p.xlim * sig_x, mean_x + p.xlim * sig_x, p.xbins)
-        xm, zm = np.meshgrid(xrange, zrange, indexing="ij")
-        zm = zm.flatten()
-        xm = xm.flatten() + np.polyval(slope, zm)
-        self.CSR_xmesh, self.CSR_zmesh = xm, zm
-        self.CSR_zrange, self.CSR_xrange_transformed = zrange, xrange
-        self._d_mesh = torch.from_numpy(np.stack([xm, zm])).to(self.device, non_blocking=True)
+        self.CSR_zrange = np.linspace(b.mean_z - p.zlim * b.sigma_z, b.mean_z + p.zlim * b.sigma_z, p.zbins)
+        self.CSR_xrange_transformed = np.linspace(mean_x - p.xlim * sig_x, mean_x + p.xlim * sig_x, p.xbins)
+        self._mesh_slope = (float(b._slope[0]), float(b._slope[1]))
+        self._mesh_axes = (Axis.make(self.CSR_xrange_transformed[0], self.CSR_xrange_transformed[-1], p.xbins),
+                           Axis.make(self.CSR_zrange[0], self.CSR_zrange[-1], p.zbins))
+        self._mesh_host = None
+
+    def _mesh_arrays(self):
+        if self._mesh_host is None:
+            xm, zm = np.meshgrid(self.CSR_xrange_transformed, self.CSR_zrange, indexing="ij")
+            zm = zm.flatten()
+            self._mesh_host = (xm.flatten() + np.polyval(np.array(self._mesh_slope), zm), zm)
+        return self._mesh_host
+
+    CSR_xmesh = property(lambda self: self._mesh_arrays()[0])
+    CSR_zmesh = property(lambda self: self._mesh_arrays()[1])
 
     def _wake_params(self):
         b, ip = self.beam, self.integration_params
@@ -279,7 +289,8 @@ class CSR2D:
         (`dE_dct`, `x_kick` are (xbins, zbins) CUDA tensors; `.cpu().numpy()` for host copies)."""
         p = self.CSR_params
         lat = self.lattice.device_tables(self.device)
-        de, kick = ops.wake_mesh(self.DF_tracker.history, lat, self._wake_params(), self._d_mesh[0], self._d_mesh[1],
+        xa, za = self._mesh_axes
+        de, kick = ops.wake_grid(self.DF_tracker.history, lat, self._wake_params(), xa, za, *self._mesh_slope,
                                  counters=getattr(self, "wake_counters", None))
         self.dE_dct = de.reshape(p.xbins, p.zbins)
         self.x_kick = kick.reshape(p.xbins, p.zbins)
@@ -291,7 +302,8 @@ class CSR2D:
         lat = self.lattice.device_tables(self.device)
         pad = max(self.count)
         send = torch.zeros((2, pad), dtype=torch.float64, device=self.device)
-        ops.wake_mesh(self.DF_tracker.history, lat, self._wake_params(), self._d_mesh[0], self._d_mesh[1],
+        xa, za = self._mesh_axes
+        ops.wake_grid(self.DF_tracker.history, lat, self._wake_params(), xa, za, *self._mesh_slope,
                       first=int(self.displ[self.rank]), count=int(self.count[self.rank]), out=send,
                       counters=getattr(self, "wake_counters", None))
         full = dist_utils.all_gather_blocks(send, self.count, n)

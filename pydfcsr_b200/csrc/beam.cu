@@ -1,7 +1,7 @@
 // beam.cu — A14 beam scalars and K5 kick application.
 //
 // dfcsr_beam_stats replaces the O(Np) numpy reductions the reference performs on the host every
-// step: np.std / np.mean / np.polyfit(z, x, 1) in Beam.update_status (beams.py:88-98,137-156,
+// step (two passes: moments about the first particle, then the statistics that need them): np.std / np.mean / np.polyfit(z, x, 1) in Beam.update_status (beams.py:88-98,137-156,
 // 201-215), the slice test of DF_tracker.get_DF (deposit.py:147-159) and the statistics of
 // x_transform used by get_CSR_mesh (CSR.py:368-374).  Three two-level deterministic reductions
 // (fixed grid, fixed summation order -> bitwise reproducible); only 16 doubles go back to the host.
@@ -15,11 +15,11 @@ namespace dfcsr {
 
 constexpr int kStatThreads = 256;
 constexpr int kStatBlocks = 148 * 4;
-constexpr int kStatVals = 6;
+constexpr int kStatVals = 7;
 
 struct StatWorkspace {
-    double partial[3][kStatBlocks][kStatVals];
-    unsigned int ticket[4];
+    double partial[2][kStatBlocks][kStatVals];
+    unsigned int ticket[4];   // must be zero before the first call; every pass leaves its ticket at zero
 };
 
 template <int NV>
@@ -69,57 +69,60 @@ __device__ __forceinline__ bool block_reduce_publish(double (&v)[NV], double (*p
     return threadIdx.x == 0;
 }
 
+// Pass A: first and second moments in ONE read of (x, z[, pz]).  Sums are taken about the first particle
+// (x[0], z[0], pz[0]) so that E[d^2] - E[d]^2 loses at most ~1 digit even for a bunch far from the origin.
 __global__ void __launch_bounds__(kStatThreads)
-stats_pass1(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ pz,
-            long long n, double* __restrict__ stats, StatWorkspace* ws) {
-    double v[3] = {0.0, 0.0, 0.0};
+stats_moments(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ pz,
+              long long n, double* __restrict__ stats, StatWorkspace* ws) {
+    const double cx = x[0], cz = z[0], cp = pz ? pz[0] : 0.0;
+    double v[kStatVals];
+#pragma unroll
+    for (int k = 0; k < kStatVals; ++k) v[k] = 0.0;
     for (long long i = (long long)blockIdx.x * kStatThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kStatThreads) {
-        v[0] += x[i];
-        v[1] += z[i];
-        if (pz) v[2] += pz[i];
+        double dx = x[i] - cx, dz = z[i] - cz;
+        v[0] += dx;
+        v[1] += dz;
+        v[2] = fma(dx, dx, v[2]);
+        v[3] = fma(dz, dz, v[3]);
+        v[4] = fma(dx, dz, v[4]);
+        if (pz) {
+            double dp = pz[i] - cp;
+            v[5] += dp;
+            v[6] = fma(dp, dp, v[6]);
+        }
     }
-    double tot[3];
-    if (block_reduce_publish<3>(v, ws->partial[0], &ws->ticket[0], tot)) {
-        stats[DFCSR_S_MEAN_X] = tot[0] / (double)n;
-        stats[DFCSR_S_MEAN_Z] = tot[1] / (double)n;
-        stats[DFCSR_S_MEAN_PZ] = tot[2] / (double)n;
+    double tot[kStatVals];
+    if (block_reduce_publish<kStatVals>(v, ws->partial[0], &ws->ticket[0], tot)) {
+        const double inv_n = 1.0 / (double)n;
+        const double ex = tot[0] * inv_n, ez = tot[1] * inv_n, ep = tot[5] * inv_n;
+        const double vxx = fmax(tot[2] * inv_n - ex * ex, 0.0);
+        const double vzz = fmax(tot[3] * inv_n - ez * ez, 0.0);
+        const double cxz = tot[4] * inv_n - ex * ez;
+        const double mx = cx + ex, mz = cz + ez;
+        stats[DFCSR_S_MEAN_X] = mx;
+        stats[DFCSR_S_MEAN_Z] = mz;
+        stats[DFCSR_S_SIGMA_X] = sqrt(vxx);     // np.std: population (ddof = 0)
+        stats[DFCSR_S_SIGMA_Z] = sqrt(vzz);
+        const double slope = cxz / vzz;           // least-squares line x = slope z + b (np.polyfit(z, x, 1))
+        stats[DFCSR_S_SLOPE] = slope;
+        stats[DFCSR_S_INTERCEPT] = mx - slope * mz;
+        stats[DFCSR_S_MEAN_PZ] = cp + ep;
+        stats[DFCSR_S_SIGMA_PZ] = sqrt(fmax(tot[6] * inv_n - ep * ep, 0.0));
         stats[DFCSR_S_N] = (double)n;
     }
 }
 
+// Pass B: statistics that need pass A's results: x_transform = x - polyval(slope, z) (CSR.py:368-372) and the
+// central slice |z| < 0.1 sigma_z of DF_tracker.get_DF (deposit.py:157-159).
 __global__ void __launch_bounds__(kStatThreads)
-stats_pass2(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ pz,
-            long long n, double* __restrict__ stats, StatWorkspace* ws) {
-    const double mx = stats[DFCSR_S_MEAN_X], mz = stats[DFCSR_S_MEAN_Z], mp = stats[DFCSR_S_MEAN_PZ];
-    double v[4] = {0.0, 0.0, 0.0, 0.0};
-    for (long long i = (long long)blockIdx.x * kStatThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kStatThreads) {
-        double dx = x[i] - mx, dz = z[i] - mz;
-        v[0] = fma(dx, dx, v[0]);
-        v[1] = fma(dz, dz, v[1]);
-        v[2] = fma(dx, dz, v[2]);
-        if (pz) {
-            double dp = pz[i] - mp;
-            v[3] = fma(dp, dp, v[3]);
-        }
-    }
-    double tot[4];
-    if (block_reduce_publish<4>(v, ws->partial[1], &ws->ticket[1], tot)) {
-        stats[DFCSR_S_SIGMA_X] = sqrt(tot[0] / (double)n);   // np.std: population (ddof = 0)
-        stats[DFCSR_S_SIGMA_Z] = sqrt(tot[1] / (double)n);
-        double slope = tot[2] / tot[1];                       // least-squares line x = slope z + b
-        stats[DFCSR_S_SLOPE] = slope;
-        stats[DFCSR_S_INTERCEPT] = mx - slope * mz;
-        stats[DFCSR_S_SIGMA_PZ] = sqrt(tot[3] / (double)n);
-    }
-}
-
-__global__ void __launch_bounds__(kStatThreads)
-stats_pass3(const double* __restrict__ x, const double* __restrict__ z, long long n,
-            double* __restrict__ stats, StatWorkspace* ws) {
+stats_residuals(const double* __restrict__ x, const double* __restrict__ z, long long n,
+                double* __restrict__ stats, StatWorkspace* ws) {
     const double mx = stats[DFCSR_S_MEAN_X], mz = stats[DFCSR_S_MEAN_Z];
     const double slope = stats[DFCSR_S_SLOPE];
     const double cut = 0.1 * stats[DFCSR_S_SIGMA_Z];
-    double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    double v[kStatVals];
+#pragma unroll
+    for (int k = 0; k < kStatVals; ++k) v[k] = 0.0;
     for (long long i = (long long)blockIdx.x * kStatThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kStatThreads) {
         double zi = z[i];
         double dx = x[i] - mx;
@@ -132,8 +135,8 @@ stats_pass3(const double* __restrict__ x, const double* __restrict__ z, long lon
             v[4] += 1.0;
         }
     }
-    double tot[5];
-    if (block_reduce_publish<5>(v, ws->partial[2], &ws->ticket[2], tot)) {
+    double tot[kStatVals];
+    if (block_reduce_publish<kStatVals>(v, ws->partial[1], &ws->ticket[1], tot)) {
         double me = tot[0] / (double)n;
         stats[DFCSR_S_MEAN_XT] = me;
         stats[DFCSR_S_SIGMA_XT] = sqrt(fmax(tot[1] / (double)n - me * me, 0.0));
@@ -203,14 +206,11 @@ extern "C" int dfcsr_beam_stats(const double* d_x, const double* d_z, const doub
     DFCSR_REQUIRE(n >= 2, "need at least two particles");
     cudaStream_t st = as_stream(stream);
     StatWorkspace* ws = reinterpret_cast<StatWorkspace*>(d_workspace);
-    DFCSR_CUDA_OK(cudaMemsetAsync(ws->ticket, 0, sizeof(ws->ticket), st));
-    DFCSR_CUDA_OK(cudaMemsetAsync(d_stats, 0, sizeof(double) * DFCSR_STATS_DOUBLES, st));
     long long want = (n + kStatThreads - 1) / kStatThreads;
     unsigned blocks = (unsigned)(want < kStatBlocks ? want : kStatBlocks);
-    stats_pass1<<<blocks, kStatThreads, 0, st>>>(d_x, d_z, d_pz, n, d_stats, ws);
-    stats_pass2<<<blocks, kStatThreads, 0, st>>>(d_x, d_z, d_pz, n, d_stats, ws);
-    stats_pass3<<<blocks, kStatThreads, 0, st>>>(d_x, d_z, n, d_stats, ws);
-    count_launch(3);
+    stats_moments<<<blocks, kStatThreads, 0, st>>>(d_x, d_z, d_pz, n, d_stats, ws);
+    stats_residuals<<<blocks, kStatThreads, 0, st>>>(d_x, d_z, n, d_stats, ws);
+    count_launch(2);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;
 }

@@ -35,14 +35,13 @@ constexpr int kMaxWindow = 33;
 constexpr int kMaxHalf = kMaxWindow / 2;
 constexpr int kPartials = 4;
 
-struct DfOps {   // device copy of the Savitzky-Golay operators
-    double taps[kMaxWindow];
-    double edge_lo[kMaxHalf * kMaxWindow];
-    double edge_hi[kMaxHalf * kMaxWindow];
+struct DfOps {   // device-resident Savitzky-Golay operators (uploaded once per (window, order) by the caller)
+    const double* taps;      // [window]
+    const double* edge_lo;   // [window/2][window]
+    const double* edge_hi;   // [window/2][window]
 };
 
 struct DfWorkspace {
-    DfOps ops;
     double partial[8][kDfMaxCtas][kPartials];
     // followed by 6 scratch planes of nx*nz doubles
 };
@@ -52,6 +51,7 @@ struct DfParams {
     const double* vxsum;
     Axis ax, az;
     int window;
+    DfOps ops;
     double velocity_threshold;
     double* fields;
     double* scalars;
@@ -155,7 +155,7 @@ __device__ __forceinline__ void make_df_body(const DfParams& P, Sync cluster) {
     const int cells = nx * nz;
     const int tid = cta * kDfThreads + threadIdx.x;
     const int nthreads = (int)gridDim.x * kDfThreads;
-    const DfOps& ops = P.ws->ops;
+    const DfOps ops = P.ops;
     const int window = P.window;
     double* T0 = P.scratch;
     double* T1 = T0 + cells;
@@ -301,11 +301,11 @@ extern "C" int64_t dfcsr_make_df_workspace(int32_t nx, int32_t nz) {
 }
 
 extern "C" int dfcsr_make_df(const double* d_count, const double* d_vxsum, dfcsr_axis x_axis, dfcsr_axis z_axis,
-                             int32_t window, const double* h_taps, const double* h_edge_lo, const double* h_edge_hi,
+                             int32_t window, const double* d_taps, const double* d_edge_lo, const double* d_edge_hi,
                              double velocity_threshold, double* d_fields, double* d_scalars, void* d_workspace,
                              void* stream) {
     DFCSR_REQUIRE(d_count && d_vxsum && d_fields && d_scalars && d_workspace, "null device pointer");
-    DFCSR_REQUIRE(h_taps && (window < 3 || (h_edge_lo && h_edge_hi)), "null operator pointer");
+    DFCSR_REQUIRE(d_taps && (window < 3 || (d_edge_lo && d_edge_hi)), "null operator pointer");
     DFCSR_REQUIRE(window >= 1 && (window & 1), "window must be odd and positive");
     if (window > kMaxWindow) {
         set_error("dfcsr_make_df: filter_window %d exceeds the supported %d", window, kMaxWindow);
@@ -316,18 +316,15 @@ extern "C" int dfcsr_make_df(const double* d_count, const double* d_vxsum, dfcsr
     DFCSR_REQUIRE((long long)x_axis.n * z_axis.n < (1LL << 30), "grid too large");
     cudaStream_t st = as_stream(stream);
     DfWorkspace* ws = reinterpret_cast<DfWorkspace*>(d_workspace);
-    const int half = window / 2;
-    DFCSR_CUDA_OK(cudaMemcpyAsync(ws->ops.taps, h_taps, sizeof(double) * window, cudaMemcpyHostToDevice, st));
-    if (half > 0) {
-        DFCSR_CUDA_OK(cudaMemcpyAsync(ws->ops.edge_lo, h_edge_lo, sizeof(double) * half * window, cudaMemcpyHostToDevice, st));
-        DFCSR_CUDA_OK(cudaMemcpyAsync(ws->ops.edge_hi, h_edge_hi, sizeof(double) * half * window, cudaMemcpyHostToDevice, st));
-    }
     DfParams P;
     P.count = d_count;
     P.vxsum = d_vxsum;
     P.ax = make_axis(x_axis.start, x_axis.stop, x_axis.n);
     P.az = make_axis(z_axis.start, z_axis.stop, z_axis.n);
     P.window = window;
+    P.ops.taps = d_taps;
+    P.ops.edge_lo = d_edge_lo;
+    P.ops.edge_hi = d_edge_hi;
     P.velocity_threshold = velocity_threshold;
     P.fields = d_fields;
     P.scalars = d_scalars;

@@ -102,6 +102,7 @@ def savgol_operators(window: int, order: int):
 
 
 _df_ws: dict = {}
+_sg_dev: dict = {}
 
 
 def make_df(count, vxsum, x_axis: Axis, z_axis: Axis, window: int, order: int, velocity_threshold: float,
@@ -116,11 +117,13 @@ def make_df(count, vxsum, x_axis: Axis, z_axis: Axis, window: int, order: int, v
     if out is None:
         out = torch.empty((5, nx, nz), dtype=F64, device=dev)
     scalars = torch.empty(_lib.DF_SCALARS, dtype=F64, device=dev)
-    taps, lo, hi = savgol_operators(window, order)
-    check(lib.dfcsr_make_df(_ptr(count), _ptr(vxsum), x_axis, z_axis, window,
-                            taps.ctypes.data_as(C.c_void_p), lo.ctypes.data_as(C.c_void_p),
-                            hi.ctypes.data_as(C.c_void_p), float(velocity_threshold), _ptr(out), _ptr(scalars),
-                            _ptr(ws), _stream()), "dfcsr_make_df")
+    key = (window, order, dev)
+    if key not in _sg_dev:          # operators are uploaded once per (window, order, device)
+        _sg_dev[key] = tuple(torch.from_numpy(a.reshape(-1).copy()).to(dev) if a.size else None
+                             for a in savgol_operators(window, order))
+    taps, lo, hi = _sg_dev[key]
+    check(lib.dfcsr_make_df(_ptr(count), _ptr(vxsum), x_axis, z_axis, window, _ptr(taps), _ptr(lo), _ptr(hi),
+                            float(velocity_threshold), _ptr(out), _ptr(scalars), _ptr(ws), _stream()), "dfcsr_make_df")
     return out, scalars
 
 
@@ -243,6 +246,20 @@ def wake_mesh(hist: DeviceHistory, lat: DeviceLattice, wp: _lib.WakeParams, xmes
     check(lib.dfcsr_wake_mesh(C.byref(hv), C.byref(lv), C.byref(wp), _ptr(_f64(xmesh, "xmesh")),
                               _ptr(_f64(zmesh, "zmesh")), first, count, _ptr(out[0]), _ptr(out[1]),
                               _ptr(counters), _stream()), "dfcsr_wake_mesh")
+    return out[0][:count], out[1][:count]
+
+
+def wake_grid(hist: DeviceHistory, lat: DeviceLattice, wp: _lib.WakeParams, x_axis: Axis, z_axis: Axis, slope, intercept,
+              first=0, count=None, out=None, counters=None):
+    """Like wake_mesh, with the observation mesh generated on the device from CSR_xrange_transformed /
+    CSR_zrange and the chirp line (CSR.py:380-389): nothing is built or uploaded on the host."""
+    n = x_axis.n * z_axis.n
+    count = n - first if count is None else count
+    if out is None:
+        out = torch.empty((2, max(count, 1)), dtype=F64, device=hist.ring.device)
+    hv, lv = hist.view(), lat.view()
+    check(lib.dfcsr_wake_grid(C.byref(hv), C.byref(lv), C.byref(wp), x_axis, z_axis, float(slope), float(intercept),
+                              first, count, _ptr(out[0]), _ptr(out[1]), _ptr(counters), _stream()), "dfcsr_wake_grid")
     return out[0][:count], out[1][:count]
 
 
