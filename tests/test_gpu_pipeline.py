@@ -129,3 +129,68 @@ def test_csr2d_step_matches_oracle():
     dbg = csr.get_CSR_wake(s_k, csr.CSR_xmesh[k], debug=True)
     tot = sum(np.trapz(np.trapz(r["integrand_z"], r["xp"], axis=0), r["sp"]) for r in dbg)
     assert abs(-csr.CSR_scaling * tot - de_k) <= 1e-10 * abs(de_k)
+
+
+def test_csr2d_full_chicane_shadowed_by_oracle():
+    """The whole 133-step chicane through CSR2D.run() on the device, shadowed step by step by the CPU
+    oracle fed with the device's particle batches: same grid-branch / window / rebuild decisions, and
+    every wake (both quadrature branches: |slope| climbs to ~100 in the middle of the chicane, then
+    falls back) within the 1e-10 gate.  Reduced sizes keep the CPU side to about a minute."""
+    import torch
+    from pydfcsr_b200 import CSR2D, synth
+    dep = dict(xbins=48, zbins=64, xlim=5, zlim=5, filter_order=1, filter_window=9, velocity_threhold=1000, upper_limit=640)
+    inp = {"input_beam": {"style": "synthetic", "n_particle": 60_000, "seed": 2},
+           "input_lattice": {"lattice_config": synth.chicane_lattice_config()},
+           "particle_deposition": dep,
+           "CSR_integration": dict(n_formation_length=1, zbins=24, xbins=24),
+           "CSR_computation": dict(compute_CSR=1, apply_CSR=1, transverse_on=1, xbins=3, zbins=4, xlim=3, zlim=3,
+                                   write_beam=None, write_wakes=False, workdir="/tmp/dfcsr_test")}
+    csr = CSR2D(inp, parallel=False, device="cuda:0", verbose=False)
+    trk = csr.DF_tracker
+    cfg = O.DepositConfig(**dep)
+    hist = O.HistoryOracle(cfg)
+    lat = scenario.lattice_tables()
+    log = dict(wakes=0, band=0, rebuilds=0, max_err=0.0, shapes=set())
+
+    # the constructor has already logged the initial beam (CSR.py:75-78): mirror it
+    c0 = csr.beam.to_host()
+    hist.append(O.make_density_functions(c0[0], c0[4], c0[1], 0, cfg))
+    hist.push(float("inf"), 1)
+
+    get_df, push, wake = trk.get_DF, trk.append_interpolant, csr.calculate_2D_CSR
+
+    def shadow_get_df(x, z, px, t, stats=None):
+        get_df(x=x, z=z, px=px, t=t, stats=stats)
+        df = O.make_density_functions(x.cpu().numpy(), z.cpu().numpy(), px.cpu().numpy(), t, cfg)
+        assert df.density.shape == tuple(trk._current.fields.shape[1:]), "grid branch (deposit.py:160-167) differs"
+        log["shapes"].add(df.density.shape)
+        hist.append(df)
+
+    def shadow_push(formation_length, n_formation_length):
+        got = push(formation_length, n_formation_length)
+        exp = hist.push(formation_length, n_formation_length)
+        assert got == exp and list(trk.time_interp) == list(hist.time_interp), "window / rebuild policy differs"
+        log["rebuilds"] += int(exp)
+        return got
+
+    def shadow_wake():
+        wake()
+        b = csr.beam
+        sc = O.WakeScalars(t=b.position, sigma_x=b._sigma_x, sigma_z=b._sigma_z, slope0=b._slope[0], mean_x=b._mean_x,
+                           formation_window=csr.integration_params.n_formation_length * csr.formation_length,
+                           csr_scaling=csr.CSR_scaling, nx=24, nz=24)
+        de, kick = O.wake_mesh(csr.CSR_xmesh, csr.CSR_zmesh, sc, lat, hist.stack())
+        g_de, g_kick = csr.dE_dct.cpu().numpy().ravel(), csr.x_kick.cpu().numpy().ravel()
+        assert np.all(np.isfinite(g_de)) and np.all(np.isfinite(g_kick))
+        err = max(_rel(g_de, de), _rel(g_kick, kick))
+        log["max_err"] = max(log["max_err"], err)
+        log["wakes"] += 1
+        log["band"] += int(abs(b._slope[0]) > 1)
+        assert err < 1e-10, (b.position, b._slope[0], err)
+
+    trk.get_DF, trk.append_interpolant, csr.calculate_2D_CSR = shadow_get_df, shadow_push, shadow_wake
+    csr.run()
+    assert csr.beam.step == 133 and abs(csr.beam.position - 13.3) < 1e-9
+    assert log["wakes"] >= 50 and log["band"] >= 10 and log["wakes"] - log["band"] >= 10, log
+    assert log["rebuilds"] >= 2 and len(log["shapes"]) == 2, log          # both deposit-grid branches were taken
+    assert csr.beam.sigma_z < 0.2 * 200e-6                                  # the chicane compressed the bunch ~10x
