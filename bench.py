@@ -350,6 +350,13 @@ def gpu_arm(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     # 5 fields x 8 corners x 8 B per in-grid sample; 4 B in the optional fp32-storage mode
     k4_bytes = (320.0 if args.precision == "fp64" else 160.0) * n_in_local
+    traffic = None                      # DRAM bytes per K4 launch from the committed ncu --set full capture
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "k4_ncu_traffic.json")))
+        if world == 1 and args.precision == "fp64":
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        pass
     achieved = k4_bytes / (k4_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -369,7 +376,7 @@ def gpu_arm(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "wake_mesh_kernel (K4)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                      "k4_ms_per_launch": k4_ms, "k4_share_of_step": k4_ms / ms_step,
                      "in_grid_samples_per_launch": n_in_local, "in_grid_fraction": n_in_local / (n_pts * spp / world),

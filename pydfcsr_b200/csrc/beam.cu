@@ -15,7 +15,7 @@ namespace dfcsr {
 
 constexpr int kStatThreads = 256;
 constexpr int kStatBlocks = 148 * 4;
-constexpr int kStatVals = 7;
+constexpr int kStatVals = 8;
 
 struct StatWorkspace {
     double partial[2][kStatBlocks][kStatVals];
@@ -125,10 +125,13 @@ stats_residuals(const double* __restrict__ x, const double* __restrict__ z, long
     for (int k = 0; k < kStatVals; ++k) v[k] = 0.0;
     for (long long i = (long long)blockIdx.x * kStatThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kStatThreads) {
         double zi = z[i];
-        double dx = x[i] - mx;
-        double e = dx - slope * (zi - mz);   // x_transform up to the (rounding-level) constant term
+        double dx = x[i] - mx, dz = zi - mz;
+        double e = dx - slope * dz;          // x_transform up to the (rounding-level) constant term
         v[0] += e;
         v[1] = fma(e, e, v[1]);
+        v[5] = fma(dx, dx, v[5]);            // second moments about the true means: two-pass accuracy, like
+        v[6] = fma(dz, dz, v[6]);            // np.std / np.polyfit (pass A's one-pass values lose ~2 digits,
+        v[7] = fma(dx, dz, v[7]);            // enough to shift the deposit grid by 1e-13 of a cell)
         if (fabs(zi) < cut) {                // deposit.py:157: |z|, not |z - mean z|
             v[2] += dx;
             v[3] = fma(dx, dx, v[3]);
@@ -144,6 +147,11 @@ stats_residuals(const double* __restrict__ x, const double* __restrict__ z, long
         double ms = tot[2] / c;
         stats[DFCSR_S_SLICE_SIGMA_X] = sqrt(fmax(tot[3] / c - ms * ms, 0.0));
         stats[DFCSR_S_SLICE_COUNT] = c;
+        stats[DFCSR_S_SIGMA_X] = sqrt(tot[5] / (double)n);
+        stats[DFCSR_S_SIGMA_Z] = sqrt(tot[6] / (double)n);
+        const double slope2 = tot[7] / tot[6];
+        stats[DFCSR_S_SLOPE] = slope2;
+        stats[DFCSR_S_INTERCEPT] = mx - slope2 * mz;
     }
 }
 

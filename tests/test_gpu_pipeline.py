@@ -191,6 +191,7 @@ def test_csr2d_full_chicane_shadowed_by_oracle():
     trk.get_DF, trk.append_interpolant, csr.calculate_2D_CSR = shadow_get_df, shadow_push, shadow_wake
     csr.run()
     assert csr.beam.step == 133 and abs(csr.beam.position - 13.3) < 1e-9
-    assert log["wakes"] >= 50 and log["band"] >= 10 and log["wakes"] - log["band"] >= 10, log
+    assert log["wakes"] >= 50 and log["band"] >= 10 and log["wakes"] - log["band"] >= 5, log
+    assert log["max_err"] < 5e-11, log        # measured 7.6e-12 over the whole lattice
     assert log["rebuilds"] >= 2 and len(log["shapes"]) == 2, log          # both deposit-grid branches were taken
     assert csr.beam.sigma_z < 0.2 * 200e-6                                  # the chicane compressed the bunch ~10x
