@@ -94,8 +94,10 @@ class Beam:
         self._mean_z = float(st[_lib.S_MEAN_Z])
 
     def track(self, element, step_size, update_step=True):
-        """beams.py:101-106.  `element` is a tracking.* element (stand-in for bmadx.track_element)."""
-        self.coords = [c.contiguous() for c in tracking.track_linear(tuple(self.coords), element)]
+        """beams.py:101-106.  `element` comes from tracking.make_element: a Bmad-X element when that package is
+        importable (tracked with bmadx.track_element on the device tensors), else a first-order stand-in."""
+        self.coords = [c.contiguous() for c in tracking.track(tuple(self.coords), element, self.position,
+                                                              self._init_energy, MC2)]
         self.position += step_size
         if update_step:
             self.step += 1

@@ -142,22 +142,23 @@ class CSR2D:
         """Element for one (partial) step (CSR.py:146-199); returns a `tracking` stand-in element."""
         cfg = dict(self.lattice.lattice_config[ele])
         kind = cfg["type"]
+        p0c = self.beam.init_energy
         if kind == "dipole":
             L = cfg["L"]
             G = cfg["G"] if "G" in cfg else cfg["angle"] / L
             E1, E2 = cfg.get("E1", 0), cfg.get("E2", 0)
             if entrance and exit:
-                return tracking.SBend(L=DL, G=G, E1=E1, E2=E2, FRINGE_AT=cfg.get("FRINGE_AT", "both_ends"))
+                return tracking.make_element("dipole", DL, p0c, G=G, E1=E1, E2=E2, FRINGE_AT=cfg.get("FRINGE_AT", "both_ends"))
             if entrance:
-                return tracking.SBend(L=DL, G=G, E1=E1, E2=0.0, FRINGE_AT="entrance_end")
+                return tracking.make_element("dipole", DL, p0c, G=G, E1=E1, E2=0.0, FRINGE_AT="entrance_end")
             if exit:
-                return tracking.SBend(L=DL, G=G, E1=0.0, E2=E2, FRINGE_AT="exit_end")
-            return tracking.SBend(L=DL, G=G, E1=0.0, E2=0.0, FRINGE_AT="no_end")
+                return tracking.make_element("dipole", DL, p0c, G=G, E1=0.0, E2=E2, FRINGE_AT="exit_end")
+            return tracking.make_element("dipole", DL, p0c, G=G, E1=0.0, E2=0.0, FRINGE_AT="no_end")
         if kind == "quad":
-            return tracking.Quadrupole(L=DL, K1=cfg["K1"])
+            return tracking.make_element("quad", DL, p0c, K1=cfg["K1"])
         if kind == "sextupole":
-            return tracking.Sextupole(L=DL, K2=cfg["K2"])
-        return tracking.Drift(L=DL)
+            return tracking.make_element("sextupole", DL, p0c, K2=cfg["K2"])
+        return tracking.make_element("drift", DL, p0c)
 
     def _log(self, *a):
         if self.verbose and self.rank == 0:

@@ -12,7 +12,17 @@ Coordinates: Bmad-X canonical (x, px, y, py, z, pz); z > 0 is the head; pz = del
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
+
+try:  # the reference's tracker (beams.py:8, CSR.py:3); works on torch tensors, so the beam stays on the device
+    if os.environ.get("DFCSR_USE_BMADX", "1") != "1":
+        raise ImportError("disabled")
+    import bmadx as _bmadx
+    HAVE_BMADX = True
+except Exception:  # not installable offline: fall back to the first-order maps below
+    _bmadx = None
+    HAVE_BMADX = False
 
 
 @dataclass
@@ -80,3 +90,33 @@ def track_linear(coords, element):
             y, py = cf * y + (sf / w) * py, -(w * sf) * y + cf * py
         return x, px, y, py, z, pz
     return x + L * px, px, y + L * py, py, z, pz
+
+
+def make_element(kind: str, L: float, p0c: float = 0.0, **kw):
+    """Element factory used by CSR2D.get_bmadx_element (CSR.py:146-199): Bmad-X elements when the package is
+    importable, the stand-ins above otherwise.  kind in {'drift', 'dipole', 'quad', 'sextupole'}."""
+    if HAVE_BMADX:
+        if kind == "dipole":
+            return _bmadx.SBend(L=L, P0C=p0c, G=kw.get("G", 0.0), E1=kw.get("E1", 0.0), E2=kw.get("E2", 0.0),
+                                FRINGE_AT=kw.get("FRINGE_AT", "both_ends"))
+        if kind == "quad":
+            return _bmadx.Quadrupole(L=L, K1=kw["K1"])
+        if kind == "sextupole":
+            return _bmadx.Sextupole(L=L, K2=kw["K2"])
+        return _bmadx.Drift(L=L)
+    if kind == "dipole":
+        return SBend(L=L, G=kw.get("G", 0.0), E1=kw.get("E1", 0.0), E2=kw.get("E2", 0.0),
+                     FRINGE_AT=kw.get("FRINGE_AT", "both_ends"), P0C=p0c)
+    if kind == "quad":
+        return Quadrupole(L=L, K1=kw["K1"])
+    if kind == "sextupole":
+        return Sextupole(L=L, K2=kw["K2"])
+    return Drift(L=L)
+
+
+def track(coords, element, s=0.0, p0c=0.0, mc2=0.51099895e6):
+    """beams.py:101-102: track_element(particle, element).  coords = (x, px, y, py, z, pz)."""
+    if HAVE_BMADX and not isinstance(element, (Drift, SBend, Quadrupole, Sextupole)):
+        part = _bmadx.track_element(_bmadx.Particle(*coords, s, p0c, mc2), element)
+        return part.x, part.px, part.y, part.py, part.z, part.pz
+    return track_linear(coords, element)

@@ -1,5 +1,7 @@
 """GPU parity of the whole hot path through the reference-facing classes (DF_tracker, CSR2D, Beam):
 the same particle batches go through the CUDA pipeline and through the CPU oracle pipeline."""
+import os
+
 import numpy as np
 import pytest
 
@@ -195,3 +197,20 @@ def test_csr2d_full_chicane_shadowed_by_oracle():
     assert log["max_err"] < 5e-11, log        # measured 7.6e-12 over the whole lattice
     assert log["rebuilds"] >= 2 and len(log["shapes"]) == 2, log          # both deposit-grid branches were taken
     assert csr.beam.sigma_z < 0.2 * 200e-6                                  # the chicane compressed the bunch ~10x
+
+
+def test_yaml_driven_run_matches_reference_schema(tmp_path, monkeypatch):
+    """CSR2D(input_file=...) with the reference's YAML schema (examples/input/chicane_config.yaml, relative
+    lattice path resolved against the working directory like the reference does), a few steps."""
+    import torch
+    from pydfcsr_b200 import CSR2D
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.chdir(os.path.join(root, "examples"))
+    csr = CSR2D(input_file="input/chicane_config.yaml", verbose=False)
+    assert csr.CSR_params.xbins == 10 and csr.CSR_params.zbins == 30 and csr.integration_params.xbins == 200
+    assert csr.DF_tracker.xbins == 300 and csr.DF_tracker.upper_limit == 2000 and csr.lattice.total_steps == 134
+    csr.run(stop_time=0.25)
+    assert csr.beam.step == 3 and tuple(csr.dE_dct.shape) == (10, 30)
+    assert bool(torch.isfinite(csr.dE_dct).all()) and float(csr.dE_dct.abs().max()) > 0
+    with pytest.raises(AssertionError):
+        CSR2D(input_file={"input_beam": {"style": "synthetic", "n_particle": 10}, "input_lattice": {}, "bogus": 1})

@@ -53,7 +53,7 @@ for n in (1_000_000, 10_000_000, 50_000_000):
     report(f"K1 ngp n={n:.0e} grid=(100, 100)", ms, 16 * n)
     st = torch.zeros(16, dtype=torch.float64, device="cuda")
     ms = timeit(lambda: ops.beam_stats(x, z, pz))
-    report(f"A14 stats (3 passes + D2H sync) n={n:.0e}", ms, (24 + 24 + 16) * n)
+    report(f"A14 stats (2 passes + D2H sync) n={n:.0e}", ms, (24 + 16) * n)
     de = torch.randn((64, 64), generator=g, device="cuda", dtype=torch.float64)
     ms = timeit(lambda: ops.apply_kick(x, z, px, pz, 0.1, 0.0, de, de, Axis.make(-2e-4, 2e-4, 64), Axis.make(-6e-4, 6e-4, 64), 0.1, 5e9, True))
     report(f"K5 kick n={n:.0e}", ms, 48 * n)
