@@ -234,8 +234,10 @@ extern "C" int dfcsr_apply_kick(const double* d_x, const double* d_z, double* d_
     if (n == 0) return DFCSR_OK;
     Axis ax = make_axis(x_axis.start, x_axis.stop, x_axis.n), az = make_axis(z_axis.start, z_axis.stop, z_axis.n);
     const double factor = step_size * 1e6 / init_energy;   // beams.py:110,117
+    // one particle per thread up to 148 x 64 CTAs (then grid-stride): the kernel is a pure stream, so memory-level
+    // parallelism comes from resident threads, not from a per-thread loop
     long long want = (n + 255) / 256;
-    unsigned blocks = (unsigned)(want < 148LL * 8 ? want : 148LL * 8);
+    unsigned blocks = (unsigned)(want < 148LL * 64 ? want : 148LL * 64);
     apply_kick_kernel<<<blocks, 256, 0, as_stream(stream)>>>(d_x, d_z, d_px, d_pz, n, slope, intercept, d_dE,
                                                            d_kick, ax, az, factor, transverse_on, 1.0 / ax.step,
                                                            1.0 / az.step);

@@ -178,6 +178,39 @@ ngp_kernel(const double* __restrict__ x, const double* __restrict__ z, long long
     }
 }
 
+// NGP with a block-private int32 tile in shared memory (native ATOMS.ADD, no CAS loop): per-CTA counts cannot
+// overflow 32 bits (a CTA sees far fewer than 2^31 particles); cells outside the centred tile and the final
+// flush use 64-bit L2 atomics.  Integer adds commute: the result is bit-exact and run-to-run reproducible.
+constexpr int kNgpTileCells = 49152;   // 192 KB of int32
+
+__global__ void __launch_bounds__(kTileThreads, 1)
+ngp_tile_kernel(const double* __restrict__ x, const double* __restrict__ z, long long n, DepGrid g, Tile t,
+                unsigned long long* __restrict__ count) {
+    extern __shared__ int ntile[];
+    const int cells = t.ni * t.nj;
+    for (int c = threadIdx.x; c < cells; c += blockDim.x) ntile[c] = 0;
+    __syncthreads();
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        double cx = __dadd_rn(__dmul_rn(__dsub_rn(x[p], g.x_start), g.inv_dx), 0.5);
+        double cz = __dadd_rn(__dmul_rn(__dsub_rn(z[p], g.z_start), g.inv_dz), 0.5);
+        double fx = floor(cx), fz = floor(cz);
+        if (fx >= 0.0 && fx < (double)g.nx && fz >= 0.0 && fz < (double)g.nz) {
+            const int i = (int)fx, j = (int)fz;
+            const int ti = i - t.i0, tj = j - t.j0;
+            if (ti >= 0 && ti < t.ni && tj >= 0 && tj < t.nj) atomicAdd(ntile + ti * t.nj + tj, 1);
+            else atomicAdd(count + (long long)i * g.nz + j, 1ULL);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < cells; c += blockDim.x) {
+        const int v = ntile[c];
+        if (v) {
+            const int ti = c / t.nj, tj = c - ti * t.nj;
+            atomicAdd(count + (long long)(t.i0 + ti) * g.nz + (t.j0 + tj), (unsigned long long)v);
+        }
+    }
+}
+
 static DepGrid make_grid(int nx, double xs, double xe, int nz, double zs, double ze) {
     DepGrid g;
     g.nx = nx;
@@ -189,8 +222,9 @@ static DepGrid make_grid(int nx, double xs, double xe, int nz, double zs, double
     return g;
 }
 
-// centred sub-rectangle with the grid's aspect ratio and at most kTileCells cells
-static Tile make_tile(int nx, int nz) {
+// centred sub-rectangle with the grid's aspect ratio and at most max_cells cells
+static Tile make_tile(int nx, int nz, int max_cells = kTileCells) {
+    const int kTileCells = max_cells;
     Tile t;
     if ((long long)nx * nz <= kTileCells) {
         t.i0 = 0; t.j0 = 0; t.ni = nx; t.nj = nz;
@@ -258,9 +292,18 @@ extern "C" int dfcsr_deposit_ngp(const double* d_x, const double* d_z, int64_t n
     DFCSR_CUDA_OK(cudaMemsetAsync(d_count, 0, (size_t)nx * nz * sizeof(int64_t), st));
     if (n == 0) return DFCSR_OK;
     DepGrid g = make_grid(nx, x_start, x_end, nz, z_start, z_end);
-    long long want = (n + 255) / 256;
-    unsigned blocks = (unsigned)(want < 148LL * 8 ? want : 148LL * 8);
-    ngp_kernel<<<blocks, 256, 0, st>>>(d_x, d_z, n, g, reinterpret_cast<unsigned long long*>(d_count));
+    if (n >= 65536) {
+        Tile t = make_tile(nx, nz, kNgpTileCells);
+        const size_t smem = (size_t)t.ni * t.nj * sizeof(int);
+        long long want = (n + kParticlesPerCta - 1) / kParticlesPerCta;
+        unsigned blocks = (unsigned)(want < 148 ? want : 148);
+        DFCSR_CUDA_OK(cudaFuncSetAttribute(ngp_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ngp_tile_kernel<<<blocks, kTileThreads, smem, st>>>(d_x, d_z, n, g, t, reinterpret_cast<unsigned long long*>(d_count));
+    } else {
+        long long want = (n + 255) / 256;
+        unsigned blocks = (unsigned)(want < 148LL * 8 ? want : 148LL * 8);
+        ngp_kernel<<<blocks, 256, 0, st>>>(d_x, d_z, n, g, reinterpret_cast<unsigned long long*>(d_count));
+    }
     count_launch(1);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;

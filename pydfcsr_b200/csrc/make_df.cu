@@ -32,7 +32,6 @@ constexpr int kDfMaxCtas = 64;    // CTAs of the cooperative launch used for lar
 constexpr int kClusterCells = 16384;
 constexpr int kDfThreads = 512;
 constexpr int kMaxWindow = 33;
-constexpr int kMaxHalf = kMaxWindow / 2;
 constexpr int kPartials = 4;
 
 struct DfOps {   // device-resident Savitzky-Golay operators (uploaded once per (window, order) by the caller)
