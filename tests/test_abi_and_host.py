@@ -133,3 +133,15 @@ def test_all_gather_blocks_world2_gloo(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "ok 0" in out.stdout and "ok 1" in out.stdout
+
+
+def test_parameter_blocks_mirror_reference_defaults():
+    """params.py:15-43: same keys/defaults; unknown keys are a TypeError like an unexpected keyword there."""
+    from pydfcsr_b200.params import CSR_params, Integration_params
+    ip = Integration_params()
+    assert (ip.n_formation_length, ip.zbins, ip.xbins) == (4, 200, 200)
+    cp = CSR_params({"xbins": 10, "write_beam": [16, 17]})
+    assert (cp.xbins, cp.zbins, cp.xlim, cp.zlim, cp.apply_CSR, cp.compute_CSR, cp.transverse_on) == (10, 30, 5, 5, 1, 1, 1)
+    assert cp.write_wakes is True and cp.write_beam == [16, 17] and os.path.isabs(cp.workdir) and cp.write_name == ""
+    with pytest.raises(TypeError):
+        CSR_params({"not_a_key": 1})
