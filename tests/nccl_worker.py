@@ -29,5 +29,5 @@ for a, b in ((par[0], csr.dE_dct), (par[1], csr.x_kick)):
 gathered = [torch.empty_like(par[0]) for _ in range(csr.world_size)]
 torch.distributed.all_gather(gathered, par[0])
 assert all(torch.equal(g, par[0]) for g in gathered), "ranks disagree"
-print("nccl ok", csr.rank, flush=True)
+os.write(1, f"nccl ok {csr.rank}\n".encode())        # one write per rank: print() pieces interleave across ranks
 torch.distributed.destroy_process_group()

@@ -117,7 +117,7 @@ for n in (7, 10, 4096):
     got = D.all_gather_blocks(send, count, n).numpy()
     assert np.array_equal(got, full), (rank, n)
 dist.barrier()
-print("ok", rank)
+open(os.path.join(sys.argv[2], f"ok{rank}"), "w").write("ok")     # one file per rank: stdout of two ranks interleaves
 '''
 
 
@@ -129,10 +129,10 @@ def test_all_gather_blocks_world2_gloo(tmp_path):
         sock.bind(("127.0.0.1", 0))
         port = sock.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), str(script), ROOT]
+           "--master-port", str(port), str(script), ROOT, str(tmp_path)]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "ok 0" in out.stdout and "ok 1" in out.stdout
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
 
 
 def test_parameter_blocks_mirror_reference_defaults():
