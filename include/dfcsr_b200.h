@@ -126,8 +126,12 @@ int dfcsr_beam_stats(const double* d_x, const double* d_z, const double* d_pz, i
 /* ---- A1 / K1 particle deposition (deposit.py:42-87, called at deposit.py:172,178) --------------
  * One pass deposits both weights (w = 1 and w = px) with CIC on an (nx, nz) grid whose bin spacing
  * is (end - start) / n.  d_count / d_vxsum (nx*nz doubles each) are zeroed by the call.
- * mode 0 = automatic, 1 = block-private shared-memory tile + warp match, 2 = direct L2 reductions,
- * 3 = block-private tile without the warp match. */
+ * mode 0 = automatic (4 for n >= 65536, else 5);
+ * 4 = 64-bit fixed-point block-private shared-memory tile, 5 = 64-bit fixed-point L2 reductions: integer
+ *     accumulation, bit-reproducible from run to run and across ranks, cell sums within ~1e-14 of the largest
+ *     cell (a non-finite px makes d_vxsum NaN everywhere and leaves d_count unaffected);
+ * 1 = fp64 tile + warp match, 2 = fp64 L2 reductions, 3 = fp64 tile (summation order, hence the last bits,
+ *     vary from run to run). */
 int dfcsr_deposit_cic(const double* d_x, const double* d_z, const double* d_px, int64_t n,
                       int32_t nx, double x_start, double x_end,
                       int32_t nz, double z_start, double z_end,

@@ -7,26 +7,30 @@
 // 0 <= index < nbins, so particles near the edge deposit partially.
 //
 // Code paths
-//   tile   : every CTA keeps a private copy of a centred sub-rectangle of BOTH grids in shared memory
-//            (up to 12288 cells = 192 KB: the whole grid for the reference's hard-coded 100x100 branch,
-//            deposit.py:164-167; the central ~+-1.9 sigma, i.e. ~88 % of a Gaussian bunch, for a 300x300
+//   fixed-point (default, modes 4/5): 64-bit integer accumulation, bit-reproducible; see below.
+//   fp64 tile (modes 1/3): every CTA keeps a private copy of a centred sub-rectangle of BOTH grids in shared
+//            memory (up to 14464 cells = 226 KB: the whole grid for the reference's hard-coded 100x100 branch,
+//            deposit.py:164-167; the central ~+-2 sigma, i.e. ~91 % of a Gaussian bunch, for a 300x300
 //            YAML grid).  Updates inside the tile are shared-memory fp64 atomics, optionally after a
 //            warp match that merges lanes hitting the same cell; the few updates outside go straight
 //            to L2 (fp64 RED).  Non-zero tile cells are flushed with fp64 L2 reductions at the end.
-//   direct : fp64 reductions (RED.ADD.F64) into the L2-resident global grids for every update.
+//   fp64 direct (mode 2): fp64 reductions (RED.ADD.F64) into the L2-resident global grids for every update.
 // fp64 atomics make the summation order run-dependent (last-bit differences only).
 //
-// Bound: 24 B / particle of HBM reads, but the unit that saturates first is the atomic path: 8 fp64
-// updates per particle at ~1 shared-memory CAS update per clock per SM (shared memory has no native
-// fp64/fp32 add on sm_100a: ATOMS.CAST.SPIN) — see DESIGN.md §4.
+// Bound: 24 B / particle of HBM reads, but the unit that saturates first is the shared-memory atomic path
+// (8 updates per particle): fp64 adds are CAS loops (ATOMS.CAST.SPIN.64, ~1.4 updates/clk/SM on a bunch),
+// the fixed-point limbs use the native 32-bit ATOMS.ADD (~3.3 updates/clk/SM) — see DESIGN.md §4.
 //
 // NGP (nearest grid point) is an extension with no reference counterpart:
 // int64 counts, bit-exact for any order.
+#include <atomic>
+#include <math_constants.h>
+
 #include "common.cuh"
 
 namespace dfcsr {
 
-constexpr int kTileCells = 12288;      // 2 grids x 8 B x 12288 = 192 KB of the 227 KB per CTA
+constexpr int kTileCells = 14464;      // 2 grids x 8 B x 14464 = 226 KB of the 227 KB per CTA
 constexpr int kTileThreads = 1024;
 constexpr long long kParticlesPerCta = 8192;
 
@@ -166,6 +170,182 @@ cic_tile_kernel(const double* __restrict__ x, const double* __restrict__ z, cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Fixed-point path (the default).  Shared memory on sm_100a has a native 32-bit integer add (ATOMS.ADD,
+// 8.5 updates/clk/SM measured with tools/atoms_probe.cu) but fp64/u64 adds are CAS loops (1.8/clk/SM, less
+// on hot cells).  Each cell is therefore a 64-bit two's-complement fixed-point number held as two 32-bit
+// limbs: add the low limb (the returned old value gives the carry), then add high limb + carry
+// (4.1 updates/clk/SM).  Integer adds commute, so the result is bit-reproducible from run to run and
+// identical on every rank, unlike fp64 atomics.
+//
+// Scales (powers of two, so the scaling itself is exact):
+//   tile   : a CTA sees at most `chunk` particles and a particle adds at most 1 (count) or max|px| (velocity
+//            sum) to one cell, so F_t = 62 - ceil(log2(chunk+1)) fraction bits cannot overflow;
+//   global : same with chunk -> n, F_g <= F_t; a tile is shifted (rounded) to F_g when it is flushed with
+//            64-bit integer L2 reductions into the output buffers, which a last kernel converts to fp64 in place.
+// max|px| comes from a reduction pass over px (absmax_kernel) into a device scratch slot.
+// Norm-wise error of a cell sum: ~4 * 2^-62 / (largest cell's share of the bunch), e.g. 1e-14 on 300x300.
+constexpr int kScratchSlots = 64;
+__device__ unsigned long long g_absmax[kScratchSlots];
+
+__global__ void __launch_bounds__(256)
+absmax_kernel(const double* __restrict__ v, long long n, unsigned long long* __restrict__ slot) {
+    double m = 0.0;
+    bool bad = false;
+#pragma unroll 8
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        const double a = fabs(v[p]);
+        bad |= !(a == a);
+        m = fmax(m, a);
+    }
+    m = warp_max(m);
+    bad = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0)     // non-negative doubles order like their bit patterns; NaN sorts above +inf
+        atomicMax(slot, bad ? 0x7ff8000000000000ULL : (unsigned long long)__double_as_longlong(m));
+}
+
+struct FixedScales {
+    int f_tile, f_glob;          // fraction bits of the count grid in the tile / in the global buffer
+};
+
+struct VxScale {
+    double tile, glob;           // 2^(f_tile - e), 2^(f_glob - e) with max|px| < 2^e; 0 if px is all zero or not finite
+};
+
+__device__ __forceinline__ VxScale vx_scale(unsigned long long wbits, FixedScales fs) {
+    const double wmax = __longlong_as_double((long long)wbits);
+    VxScale s;
+    s.tile = 0.0;
+    s.glob = 0.0;
+    if (wmax > 0.0 && wmax < CUDART_INF) {
+        int e = ilogb(wmax) + 1;
+        e = e < -900 ? -900 : e;
+        s.tile = scalbn(1.0, fs.f_tile - e);
+        s.glob = scalbn(1.0, fs.f_glob - e);
+    }
+    return s;
+}
+
+// low limbs of all cells first, then the high limbs: consecutive cells fall in consecutive banks for both
+__device__ __forceinline__ void fixed_add_shared(unsigned* lo_limb, unsigned* hi_limb, long long q) {
+    const unsigned lo = (unsigned)q, hi = (unsigned)((unsigned long long)q >> 32);
+    const unsigned old = atomicAdd(lo_limb, lo);
+    atomicAdd(hi_limb, hi + ((unsigned)(old + lo) < lo ? 1u : 0u));
+}
+
+// Same update with the conversion done by the adder: rn(c * scale) + 1.5 * 2^52 puts the integer (|q| <= 2^50)
+// into the mantissa, so the limbs are the two words of the sum minus the constant's high word.  One DFMA
+// and one IADD instead of DMUL + F2I.S64 + shifts.
+constexpr double kMagic = 6755399441055744.0;          // 2^52 + 2^51 = 0x4338000000000000
+__device__ __forceinline__ void fixed_add_shared_fma(unsigned* lo_limb, unsigned* hi_limb, double c, double scale) {
+    const double m = __fma_rn(c, scale, kMagic);
+    const unsigned lo = (unsigned)__double2loint(m), hi = (unsigned)__double2hiint(m) - 0x43380000u;
+    const unsigned old = atomicAdd(lo_limb, lo);
+    atomicAdd(hi_limb, hi + ((unsigned)(old + lo) < lo ? 1u : 0u));
+}
+
+template <bool kTile>
+__device__ __forceinline__ void fixed_corner(const DepGrid& g, const Tile& t, unsigned* tile, int cells,
+                                             unsigned long long* __restrict__ count, unsigned long long* __restrict__ vxsum,
+                                             int i, int j, double c, double v, double sc_t, double sc_g,
+                                             double sv_t, double sv_g) {
+    if (i < 0 || i >= g.nx || j < 0 || j >= g.nz) return;     // the reference's per-corner guards
+    if (kTile) {
+        const int ti = i - t.i0, tj = j - t.j0;
+        if (ti >= 0 && ti < t.ni && tj >= 0 && tj < t.nj) {
+            const int o = ti * t.nj + tj;
+            fixed_add_shared(tile + o, tile + 2 * cells + o, __double2ll_rn(c * sc_t));
+            fixed_add_shared(tile + cells + o, tile + 3 * cells + o, __double2ll_rn(v * sv_t));
+            return;
+        }
+    }
+    const long long o = (long long)i * g.nz + j;
+    atomicAdd(count + o, (unsigned long long)__double2ll_rn(c * sc_g));
+    atomicAdd(vxsum + o, (unsigned long long)__double2ll_rn(v * sv_g));
+}
+
+template <bool kTile>
+__global__ void __launch_bounds__(kTile ? kTileThreads : 256, kTile ? 1 : 4)
+cic_fixed_kernel(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ px,
+                 long long n, DepGrid g, Tile t, FixedScales fs, const unsigned long long* __restrict__ wslot,
+                 unsigned long long* __restrict__ count, unsigned long long* __restrict__ vxsum) {
+    extern __shared__ unsigned ftile[];
+    const int cells = kTile ? t.ni * t.nj : 0;
+    if (kTile) {
+        for (int c = threadIdx.x; c < 4 * cells; c += blockDim.x) ftile[c] = 0u;
+        __syncthreads();
+    }
+    const VxScale vs = vx_scale(*wslot, fs);
+    const double sc_t = scalbn(1.0, fs.f_tile), sc_g = scalbn(1.0, fs.f_glob);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double xn = 0.0, zn = 0.0, wn = 0.0;
+    if (p < n) { xn = x[p]; zn = z[p]; wn = px[p]; }
+    while (p < n) {
+        const double xc = xn, zc = zn, w = wn;
+        p += stride;
+        if (p < n) { xn = x[p]; zn = z[p]; wn = px[p]; }      // next particle in flight while this one deposits
+        const CicSample s = cic_cell(g, xc, zc);
+        const double a_hi = 1.0 - s.a_lo, b_hi = 1.0 - s.b_lo;
+        const double c00 = s.a_lo * s.b_lo, c01 = s.a_lo * b_hi, c10 = a_hi * s.b_lo, c11 = a_hi * b_hi;
+        if (kTile) {
+            const int ti = s.i - t.i0, tj = s.j - t.j0;
+            if (ti >= 0 && ti + 1 < t.ni && tj >= 0 && tj + 1 < t.nj) {     // all four corners inside the tile
+                unsigned* cc = ftile + ti * t.nj + tj;       // count: low limbs, +2*cells high; velocity sum at +cells
+                unsigned* vv = cc + cells;
+                const int hi = 2 * cells;
+                fixed_add_shared_fma(cc, cc + hi, c00, sc_t);
+                fixed_add_shared_fma(cc + 1, cc + hi + 1, c01, sc_t);
+                fixed_add_shared_fma(cc + t.nj, cc + hi + t.nj, c10, sc_t);
+                fixed_add_shared_fma(cc + t.nj + 1, cc + hi + t.nj + 1, c11, sc_t);
+                fixed_add_shared_fma(vv, vv + hi, w * c00, vs.tile);
+                fixed_add_shared_fma(vv + 1, vv + hi + 1, w * c01, vs.tile);
+                fixed_add_shared_fma(vv + t.nj, vv + hi + t.nj, w * c10, vs.tile);
+                fixed_add_shared_fma(vv + t.nj + 1, vv + hi + t.nj + 1, w * c11, vs.tile);
+                continue;
+            }
+        }
+        fixed_corner<kTile>(g, t, ftile, cells, count, vxsum, s.i, s.j, c00, w * c00, sc_t, sc_g, vs.tile, vs.glob);
+        fixed_corner<kTile>(g, t, ftile, cells, count, vxsum, s.i, s.j + 1, c01, w * c01, sc_t, sc_g, vs.tile, vs.glob);
+        fixed_corner<kTile>(g, t, ftile, cells, count, vxsum, s.i + 1, s.j, c10, w * c10, sc_t, sc_g, vs.tile, vs.glob);
+        fixed_corner<kTile>(g, t, ftile, cells, count, vxsum, s.i + 1, s.j + 1, c11, w * c11, sc_t, sc_g, vs.tile, vs.glob);
+    }
+    if (kTile) {
+        __syncthreads();
+        const int shift = fs.f_tile - fs.f_glob;
+        const long long half = shift > 0 ? (1LL << (shift - 1)) : 0;
+        // every CTA starts its sweep somewhere else, so that the CTAs do not queue on the same L2 lines
+        const int start = (int)(((long long)blockIdx.x * 2 * cells) / gridDim.x);
+        for (int k = threadIdx.x; k < 2 * cells; k += blockDim.x) {
+            const int c = k + start < 2 * cells ? k + start : k + start - 2 * cells;
+            const long long v64 = (long long)(((unsigned long long)ftile[2 * cells + c] << 32) | ftile[c]);
+            const long long q = (v64 + half) >> shift;                     // round to the global scale
+            if (q != 0) {
+                const int cc = c < cells ? c : c - cells;
+                const int ti = cc / t.nj, tj = cc - ti * t.nj;
+                const long long o = (long long)(t.i0 + ti) * g.nz + (t.j0 + tj);
+                atomicAdd((c < cells ? count : vxsum) + o, (unsigned long long)q);
+            }
+        }
+    }
+}
+
+// int64 fixed point -> fp64, in place
+__global__ void __launch_bounds__(256)
+cic_fixed_finish(long long cells, FixedScales fs, const unsigned long long* __restrict__ wslot,
+                 double* __restrict__ count, double* __restrict__ vxsum) {
+    const unsigned long long wbits = *wslot;
+    const VxScale vs = vx_scale(wbits, fs);
+    const double inv_c = scalbn(1.0, -fs.f_glob);
+    const double wmax = __longlong_as_double((long long)wbits);
+    const bool finite = wmax < CUDART_INF;      // false for inf and NaN
+    const double inv_v = vs.glob > 0.0 ? 1.0 / vs.glob : 0.0;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (long long)gridDim.x * blockDim.x) {
+        count[c] = (double)__double_as_longlong(count[c]) * inv_c;
+        vxsum[c] = finite ? (double)__double_as_longlong(vxsum[c]) * inv_v : CUDART_NAN;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 ngp_kernel(const double* __restrict__ x, const double* __restrict__ z, long long n, DepGrid g,
            unsigned long long* __restrict__ count) {
@@ -241,6 +421,59 @@ static Tile make_tile(int nx, int nz, int max_cells = kTileCells) {
     return t;
 }
 
+static int bits_for(long long v) {      // smallest b with 2^b > v
+    int b = 0;
+    while ((1LL << b) <= v) ++b;
+    return b;
+}
+
+static std::atomic<unsigned> g_next_slot{0};
+
+// absmax(px) -> fixed-point deposit -> in-place conversion to fp64 (3 launches)
+static int deposit_fixed(const double* d_x, const double* d_z, const double* d_px, long long n, const DepGrid& g,
+                         double* d_count, double* d_vxsum, bool tiled, cudaStream_t st) {
+    unsigned long long* slots = nullptr;
+    DFCSR_CUDA_OK(cudaGetSymbolAddress(reinterpret_cast<void**>(&slots), g_absmax));
+    unsigned long long* slot = slots + (g_next_slot.fetch_add(1) % kScratchSlots);
+    DFCSR_CUDA_OK(cudaMemsetAsync(slot, 0, sizeof(unsigned long long), st));
+    {
+        long long want = (n + 2047) / 2048;
+        unsigned blocks = (unsigned)(want < 148LL * 8 ? (want < 1 ? 1 : want) : 148LL * 8);
+        absmax_kernel<<<blocks, 256, 0, st>>>(d_px, n, slot);
+    }
+    FixedScales fs;
+    fs.f_glob = 62 - bits_for(n);
+    unsigned long long* c64 = reinterpret_cast<unsigned long long*>(d_count);
+    unsigned long long* v64 = reinterpret_cast<unsigned long long*>(d_vxsum);
+    if (tiled) {
+        Tile t = make_tile(g.nx, g.nz);
+        const size_t smem = (size_t)2 * t.ni * t.nj * sizeof(double);
+        long long want = (n + kParticlesPerCta - 1) / kParticlesPerCta;
+        unsigned blocks = (unsigned)(want < 148 ? (want < 1 ? 1 : want) : 148);
+        const long long stride = (long long)blocks * kTileThreads;
+        fs.f_tile = 62 - bits_for(((n + stride - 1) / stride) * kTileThreads);
+        fs.f_tile = fs.f_tile > 50 ? 50 : fs.f_tile;          // |q| <= 2^50 for the mantissa trick of fixed_add_shared_fma
+        fs.f_glob = fs.f_glob > fs.f_tile ? fs.f_tile : fs.f_glob;
+        DFCSR_CUDA_OK(cudaFuncSetAttribute(cic_fixed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cic_fixed_kernel<true><<<blocks, kTileThreads, smem, st>>>(d_x, d_z, d_px, n, g, t, fs, slot, c64, v64);
+    } else {
+        Tile t = {0, 0, 0, 0};
+        fs.f_tile = fs.f_glob;
+        long long want = (n + 255) / 256;
+        unsigned blocks = (unsigned)(want < 148LL * 4 ? want : 148LL * 4);
+        cic_fixed_kernel<false><<<blocks, 256, 0, st>>>(d_x, d_z, d_px, n, g, t, fs, slot, c64, v64);
+    }
+    {
+        const long long cells = (long long)g.nx * g.nz;
+        long long want = (cells + 255) / 256;
+        unsigned blocks = (unsigned)(want < 148LL * 4 ? want : 148LL * 4);
+        cic_fixed_finish<<<blocks, 256, 0, st>>>(cells, fs, slot, d_count, d_vxsum);
+    }
+    count_launch(3);
+    DFCSR_CUDA_OK(cudaGetLastError());
+    return DFCSR_OK;
+}
+
 }  // namespace dfcsr
 
 using namespace dfcsr;
@@ -251,14 +484,16 @@ extern "C" int dfcsr_deposit_cic(const double* d_x, const double* d_z, const dou
     DFCSR_REQUIRE(d_count && d_vxsum && (n == 0 || (d_x && d_z && d_px)), "null pointer");
     DFCSR_REQUIRE(nx >= 1 && nz >= 1 && n >= 0, "bad sizes");
     DFCSR_REQUIRE((long long)nx * nz < (1LL << 30), "grid too large");
-    DFCSR_REQUIRE(mode >= 0 && mode <= 3, "mode must be 0 (auto), 1 (tile + warp match), 2 (direct) or 3 (tile)");
+    DFCSR_REQUIRE(mode >= 0 && mode <= 5,
+                  "mode must be 0 (auto), 1 (tile + warp match), 2 (direct), 3 (tile), 4 (fixed-point tile) or 5 (fixed-point direct)");
     cudaStream_t st = as_stream(stream);
     const size_t cells = (size_t)nx * nz;
     DFCSR_CUDA_OK(cudaMemsetAsync(d_count, 0, cells * sizeof(double), st));
     DFCSR_CUDA_OK(cudaMemsetAsync(d_vxsum, 0, cells * sizeof(double), st));
     if (n == 0) return DFCSR_OK;
     DepGrid g = make_grid(nx, x_start, x_end, nz, z_start, z_end);
-    if (mode == 0) mode = (n >= 65536) ? 3 : 2;
+    if (mode == 0) mode = (n >= 65536) ? 4 : 5;
+    if (mode >= 4) return deposit_fixed(d_x, d_z, d_px, n, g, d_count, d_vxsum, mode == 4, st);
     if (mode == 2) {
         long long want = (n + 255) / 256;
         unsigned blocks = (unsigned)(want < 148LL * 8 ? want : 148LL * 8);

@@ -63,7 +63,8 @@ def beam_stats(x: torch.Tensor, z: torch.Tensor, pz: torch.Tensor | None = None)
 # K1 deposit
 # ---------------------------------------------------------------------------------------------
 def deposit_cic(x, z, px, nx, x_start, x_end, nz, z_start, z_end, mode=0, out=None):
-    """(count, vxsum): the two CIC grids of deposit.py:172-182 in one pass."""
+    """(count, vxsum): the two CIC grids of deposit.py:172-182 in one pass.  mode 0/4/5: fixed-point, bit-reproducible
+    (default); 1/2/3: fp64 atomics (include/dfcsr_b200.h)."""
     if out is None:
         out = torch.empty((2, nx, nz), dtype=F64, device=x.device)
     check(lib.dfcsr_deposit_cic(_ptr(_f64(x, "x")), _ptr(_f64(z, "z")), _ptr(_f64(px, "px")), x.numel(),

@@ -45,7 +45,7 @@ def test_beam_stats(dev, tilt):
     assert abs(st[_lib.S_MEAN_XT]) < 1e-12 * np.std(x)
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("shape", [(100, 100), (37, 53), (300, 200)])
 def test_deposit_cic(dev, mode, shape):
     from pydfcsr_b200 import ops, synth
@@ -72,6 +72,37 @@ def test_deposit_cic_empty_and_single(dev):
     cnt, _ = ops.deposit_cic(one, one, one, 8, 0.0, 1.0, 8, 0.0, 1.0)
     ref = O.cic_deposit_2d(np.array([0.5]), np.array([0.5]), np.ones(1), 8, 0.0, 1.0, 8, 0.0, 1.0)
     assert np.array_equal(cnt.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("n", [3_000, 400_000])
+def test_deposit_cic_fixed_point_is_reproducible_and_tight(dev, n):
+    """The default (64-bit fixed-point) deposit: integer adds commute, so two runs agree bit for bit, and the
+    quantisation stays at the 1e-14 level of the largest cell.  Zero and non-finite weights are handled."""
+    import torch
+    from pydfcsr_b200 import ops, synth
+    b = synth.gaussian_bunch(n, seed=11, tilt=1.5)
+    x, px, z = b[0], b[1], b[4]
+    args = (300, np.mean(x) - 4 * np.std(x), np.mean(x) + 4 * np.std(x), 300, np.mean(z) - 4 * np.std(z), np.mean(z) + 4 * np.std(z))
+    dx, dz, dp = _up(x, dev), _up(z, dev), _up(px, dev)
+    c1, v1 = (t.clone() for t in ops.deposit_cic(dx, dz, dp, *args))
+    c2, v2 = ops.deposit_cic(dx, dz, dp, *args)
+    assert torch.equal(c1, c2) and torch.equal(v1, v2)
+    ref_c = O.cic_deposit_2d(x, z, np.ones_like(x), *args)
+    ref_v = O.cic_deposit_2d(x, z, px, *args)
+    assert _rel(c1.cpu().numpy(), ref_c) < 2e-13 and _rel(v1.cpu().numpy(), ref_v) < 2e-13
+    # a permutation of the particles gives the same bits (the fp64-atomic modes only agree to rounding)
+    perm = torch.randperm(n, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    c3, v3 = ops.deposit_cic(dx[perm].contiguous(), dz[perm].contiguous(), dp[perm].contiguous(), *args)
+    if n >= 65536:      # same tile decomposition: the per-CTA rounding to the global scale depends on who owns what
+        assert _rel(c3.cpu().numpy(), c1.cpu().numpy()) < 1e-13
+    else:
+        assert torch.equal(c3, c1) and torch.equal(v3, v1)
+    c0, v0 = ops.deposit_cic(dx, dz, torch.zeros_like(dp), *args)
+    assert torch.equal(c0, c1) and float(v0.abs().max()) == 0.0
+    bad = dp.clone()
+    bad[n // 2] = float("inf")
+    cb, vb = ops.deposit_cic(dx, dz, bad, *args)
+    assert torch.equal(cb, c1) and bool(torch.isnan(vb).all())
 
 
 def test_deposit_ngp_bit_exact(dev):

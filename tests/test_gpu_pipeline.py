@@ -133,6 +133,31 @@ def test_csr2d_step_matches_oracle():
     assert abs(-csr.CSR_scaling * tot - de_k) <= 1e-10 * abs(de_k)
 
 
+def test_run_is_bit_reproducible():
+    """Fixed-point deposit, ticketed reductions and fixed-order quadrature: two runs of the same input give
+    the same bits for the wake grids and for the kicked particles (the reference's serial numba path is
+    reproducible as well; fp64 atomics would not be)."""
+    import torch
+    from pydfcsr_b200 import CSR2D, synth
+    elements = [(n, k, L, a, e1, e2, 2) for (n, k, L, a, e1, e2, _s) in synth.CHICANE_ELEMENTS[:3]]
+
+    def run():
+        inp = {"input_beam": {"style": "synthetic", "n_particle": 150_000, "seed": 4},
+               "input_lattice": {"lattice_config": synth.chicane_lattice_config(elements=elements)},
+               "particle_deposition": dict(scenario.DEPOSIT_CFG),
+               "CSR_integration": dict(n_formation_length=1, zbins=40, xbins=40),
+               "CSR_computation": dict(compute_CSR=1, apply_CSR=1, transverse_on=1, xbins=5, zbins=7, xlim=3, zlim=3,
+                                       write_beam=None, write_wakes=False, workdir="/tmp/dfcsr_test")}
+        csr = CSR2D(inp, parallel=False, device="cuda:0", verbose=False)
+        csr.run()
+        return csr.dE_dct.clone(), csr.x_kick.clone(), torch.stack(csr.beam.coords)
+
+    a, b = run(), run()
+    assert float(a[0].abs().max()) > 0
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+
+
 def test_csr2d_full_chicane_shadowed_by_oracle():
     """The whole 133-step chicane through CSR2D.run() on the device, shadowed step by step by the CPU
     oracle fed with the device's particle batches: same grid-branch / window / rebuild decisions, and
