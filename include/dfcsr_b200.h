@@ -205,6 +205,17 @@ int dfcsr_apply_kick(const double* d_x, const double* d_z, double* d_px, double*
                      const double* d_dE, const double* d_kick, dfcsr_axis x_axis, dfcsr_axis z_axis,
                      double step_size, double init_energy, int32_t transverse_on, void* stream);
 
+/* ---- 2-D Savitzky-Golay operator (SGolay_filter.py:3-81) ---------------------
+ * sgolay2d(z, window_size, order, derivative): d_z (rows x cols, row-major) is extended by window/2
+ * samples per side with the reference's reflection rule (SGolay_filter.py:36-65) and convolved
+ * ('valid', i.e. kernel flipped like scipy.signal.fftconvolve) with n_kernels window x window kernels
+ * d_kernels[n_kernels][window][window] — the arrays the reference passes to fftconvolve: pinv(A)[0] for
+ * smoothing, -pinv(A)[1] ('col'), -pinv(A)[2] ('row').  d_out[n_kernels][rows][cols].
+ * window odd, <= 25, rows and cols >= window, n_kernels 1..3.  Not called by CSR2D.run (it is dead code in
+ * the reference's run loop too, deposit.py:187,194,227,232). */
+int dfcsr_sgolay2d(const double* d_z, int32_t rows, int32_t cols, int32_t window,
+                   const double* d_kernels, int32_t n_kernels, double* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

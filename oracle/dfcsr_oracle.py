@@ -127,6 +127,84 @@ def savgol_separable(a, window, order):
 
 
 # --------------------------------------------------------------------------------------------
+# (f)4  true 2-D Savitzky-Golay filter (SGolay_filter.py:3-81; dead code in the reference's run loop,
+#       deposit.py:187,194,227,232 — kept as an optional operator)
+# --------------------------------------------------------------------------------------------
+def sgolay2d_kernels(window: int, order: int):
+    """The three convolution kernels the reference hands to ``fftconvolve`` (SGolay_filter.py:68-81):
+    [0] smoothing, [1] minus the d/d(axis 0) fit coefficient ('col'), [2] minus the d/d(axis 1)
+    coefficient ('row').  Least-squares fit of all monomials a^p b^q, p+q <= order, on the window."""
+    if window % 2 == 0:
+        raise ValueError("window_size must be odd")
+    if window ** 2 < (order + 1) * (order + 2) / 2.0:
+        raise ValueError("order is too high for the window size")
+    half = window // 2
+    a, b = np.meshgrid(np.arange(-half, half + 1, dtype=np.float64), np.arange(-half, half + 1, dtype=np.float64),
+                       indexing="ij")                       # a: axis 0 offset (slow), b: axis 1 offset
+    a, b = a.ravel(), b.ravel()
+    # column order of the reference: total degree k ascending, then the axis-1 power n = 0..k  (SGolay_filter.py:24)
+    cols = [(a ** (k - n)) * (b ** n) for k in range(order + 1) for n in range(k + 1)]
+    pinv = np.linalg.pinv(np.stack(cols, axis=1))
+    smooth = pinv[0].reshape(window, window)
+    if order < 1:
+        return np.stack([smooth, np.zeros_like(smooth), np.zeros_like(smooth)])
+    return np.stack([smooth, -pinv[1].reshape(window, window), -pinv[2].reshape(window, window)])
+
+
+def sgolay2d_pad(z, half: int):
+    """Border extension of SGolay_filter.py:36-65: odd reflection with an absolute value, '-' on the
+    low sides and '+' on the high sides; the top-right and bottom-left corners are built from the
+    already padded right / bottom bands (the reference's own asymmetry)."""
+    z = np.asarray(z, dtype=np.float64)
+    H, W = z.shape
+    h = half
+    if h == 0:
+        return z.copy()
+    if H < 2 * h + 1 or W < 2 * h + 1:
+        raise ValueError("array smaller than the window")
+    Z = np.zeros((H + 2 * h, W + 2 * h))
+    Z[h:H + h, h:W + h] = z
+    top, bot, left, right = z[0, :], z[-1, :], z[:, :1], z[:, -1:]
+    Z[:h, h:W + h] = top - np.abs(z[h:0:-1, :] - top)
+    Z[H + h:, h:W + h] = bot + np.abs(z[H - 2:H - 2 - h:-1, :] - bot)
+    Z[h:H + h, :h] = left - np.abs(z[:, h:0:-1] - left)
+    Z[h:H + h, W + h:] = right + np.abs(z[:, W - 2:W - 2 - h:-1] - right)
+    Z[:h, :h] = z[0, 0] - np.abs(z[h:0:-1, h:0:-1] - z[0, 0])
+    Z[H + h:, W + h:] = z[-1, -1] + np.abs(z[H - 2:H - 2 - h:-1, W - 2:W - 2 - h:-1] - z[-1, -1])
+    band = Z[h, W + h:]                                                     # right band of row 0
+    Z[:h, W + h:] = band - np.abs(Z[2 * h:h:-1, W + h:] - band)
+    band = Z[H + h:, h:h + 1]                                               # bottom band of column 0
+    Z[H + h:, :h] = band - np.abs(Z[H + h:, 2 * h:h:-1] - band)
+    return Z
+
+
+def sgolay2d(z, window: int, order: int, derivative=None):
+    """sgolay2d(z, window_size, order, derivative) of SGolay_filter.py:3 with the 'valid' convolution
+    written as a direct sum (the reference uses an FFT convolution: same numbers to ~1e-16 of the
+    largest term)."""
+    ker = sgolay2d_kernels(window, order)
+    Z = sgolay2d_pad(z, window // 2)
+    H, W = np.asarray(z).shape
+
+    def conv(k):
+        out = np.zeros((H, W))
+        for a in range(window):
+            for b in range(window):
+                out += k[a, b] * Z[window - 1 - a:window - 1 - a + H, window - 1 - b:window - 1 - b + W]
+        return out
+
+    if derivative is None:
+        return conv(ker[0])
+    if derivative == "col":
+        return conv(ker[1])
+    if derivative == "row":
+        return conv(ker[2])
+    if derivative == "both":
+        return conv(ker[1]), conv(ker[2])
+    raise ValueError("derivative must be None, 'col', 'row' or 'both'")
+
+
+# --------------------------------------------------------------------------------------------
 # A3  np.gradient with coordinate arrays (deposit.py:212-213; numpy/lib/_function_base_impl.py)
 # --------------------------------------------------------------------------------------------
 def gradient_axis(f, coords, axis):

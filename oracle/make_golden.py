@@ -114,6 +114,27 @@ def golden_wake():
         print(name, "max|dE|", np.max(np.abs(csr.dE_dct)), "slope", beam._slope[0])
 
 
+def sgolay2d_input():
+    """Seeded input of the sgolay2d fixture: the CIC density of a tilted bunch on a 48 x 70 grid (serial oracle
+    deposit, so the array is reproducible to the bit)."""
+    from oracle import dfcsr_oracle as O
+    b = synth.gaussian_bunch(60_000, seed=21, tilt=1.0)
+    x, z = b[0], b[4]
+    return O.cic_deposit_2d(x, z, np.ones_like(x), 48, np.mean(x) - 4 * np.std(x), np.mean(x) + 4 * np.std(x),
+                            70, np.mean(z) - 4 * np.std(z), np.mean(z) + 4 * np.std(z))
+
+
+def golden_sgolay2d():
+    refstub.load_reference()
+    from pyDFCSR_2D.SGolay_filter import sgolay2d
+    z = sgolay2d_input()
+    out = {}
+    for window, order in ((7, 2), (5, 3)):
+        out[f"smooth_{window}_{order}"] = sgolay2d(z, window, order)
+        out[f"col_{window}_{order}"], out[f"row_{window}_{order}"] = sgolay2d(z, window, order, derivative="both")
+    np.savez(os.path.join(OUT, "sgolay2d.npz"), cases=np.array([(7, 2), (5, 3)]), checksum=float(z.sum()), **out)
+
+
 def golden_mpi_split():
     """test/test_mpi.py:14-17 evaluated for a few (work_size, ranks) pairs."""
     rows = []
@@ -133,4 +154,5 @@ if __name__ == "__main__":
     golden_df()
     golden_wake()
     golden_mpi_split()
+    golden_sgolay2d()
     print("golden vectors written to", OUT)

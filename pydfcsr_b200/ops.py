@@ -129,6 +129,57 @@ def make_df(count, vxsum, x_axis: Axis, z_axis: Axis, window: int, order: int, v
 
 
 # ---------------------------------------------------------------------------------------------
+# 2-D Savitzky-Golay operator (SGolay_filter.py:3-81)
+# ---------------------------------------------------------------------------------------------
+_sg2_cache: dict = {}
+
+
+def sgolay2d_kernels(window_size: int, order: int) -> np.ndarray:
+    """(3, w, w) host kernels: smoothing, 'col' and 'row' derivative stencils, signs as the reference passes
+    them to fftconvolve (SGolay_filter.py:68-81).  Same ValueErrors as the reference (SGolay_filter.py:10-14)."""
+    key = (window_size, order)
+    if key not in _sg2_cache:
+        if window_size % 2 == 0:
+            raise ValueError("window_size must be odd")
+        n_terms = (order + 1) * (order + 2) / 2.0
+        if window_size ** 2 < n_terms:
+            raise ValueError("order is too high for the window size")
+        off = np.arange(-(window_size // 2), window_size // 2 + 1, dtype=np.float64)
+        u = np.repeat(off, window_size)          # offset along axis 0 of every window sample
+        v = np.tile(off, window_size)            # offset along axis 1
+        design = np.stack([u ** (k - n) * v ** n for k in range(order + 1) for n in range(k + 1)], axis=1)
+        fit = np.linalg.pinv(design)
+        ker = np.zeros((3, window_size, window_size))
+        ker[0] = fit[0].reshape(window_size, window_size)
+        if order >= 1:
+            ker[1] = -fit[1].reshape(window_size, window_size)
+            ker[2] = -fit[2].reshape(window_size, window_size)
+        _sg2_cache[key] = ker
+    return _sg2_cache[key]
+
+
+def sgolay2d(z: torch.Tensor, window_size: int, order: int, derivative=None):
+    """sgolay2d(z, window_size, order, derivative) of the reference on a CUDA float64 (rows, cols) tensor:
+    smoothed array for derivative=None, one array for 'col' / 'row', a pair for 'both'."""
+    pick = {None: [0], "col": [1], "row": [2], "both": [1, 2]}
+    if derivative not in pick:
+        raise ValueError("derivative must be None, 'col', 'row' or 'both'")
+    if derivative is not None and order < 1:
+        raise ValueError("derivatives need order >= 1")
+    z = _f64(z, "z")
+    rows, cols = z.shape
+    key = (window_size, order, derivative, z.device)
+    if key not in _sg2_cache:       # stencils are uploaded once per (window, order, derivative, device)
+        ker = sgolay2d_kernels(window_size, order)[pick[derivative]]
+        _sg2_cache[key] = torch.from_numpy(np.ascontiguousarray(ker)).to(z.device)
+    d_ker = _sg2_cache[key]
+    out = torch.empty((d_ker.shape[0], rows, cols), dtype=F64, device=z.device)
+    check(lib.dfcsr_sgolay2d(_ptr(z), rows, cols, window_size, _ptr(d_ker), d_ker.shape[0], _ptr(out), _stream()),
+          "dfcsr_sgolay2d")
+    return (out[0], out[1]) if derivative == "both" else out[0]
+
+
+# ---------------------------------------------------------------------------------------------
 # K3 history
 # ---------------------------------------------------------------------------------------------
 def voxel_format(t: torch.Tensor) -> int:

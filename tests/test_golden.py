@@ -112,7 +112,7 @@ def test_gpu_cic_golden():
     g = np.load(os.path.join(G, "cic.npz"))
     b = _bunch(g)
     xs, xe, zs, ze = (float(v) for v in g["bounds"])
-    for mode in (1, 2):
+    for mode in (0, 1, 2, 4, 5):
         c, v = ops.deposit_cic(_up(b[0]), _up(b[4]), _up(b[1]), 37, xs, xe, 53, zs, ze, mode=mode)
         assert _rel(c.cpu().numpy(), g["count"]) < 1e-12 and _rel(v.cpu().numpy(), g["vxsum"]) < 1e-11
 
@@ -170,3 +170,35 @@ def test_gpu_wake_golden(case):
     k = int(g["kick_stride"])
     assert _rel(dpz.cpu().numpy()[::k] - pz[::k], g["pz_new"] - pz[::k]) < 1e-10
     assert _rel(dpx.cpu().numpy()[::k] - px[::k], g["px_new"] - px[::k]) < 1e-10
+
+
+# ------------------------------------------------------------------------- 2-D Savitzky-Golay (SGolay_filter.py)
+def _sgolay_cases():
+    from oracle.make_golden import sgolay2d_input
+    g = np.load(os.path.join(G, "sgolay2d.npz"))
+    z = sgolay2d_input()
+    assert float(z.sum()) == float(g["checksum"])        # same seeded input as the generating run
+    return z, g
+
+
+def test_oracle_sgolay2d_golden():
+    z, g = _sgolay_cases()
+    for window, order in g["cases"]:
+        window, order = int(window), int(order)
+        assert _rel(O.sgolay2d(z, window, order), g[f"smooth_{window}_{order}"]) < 1e-13
+        col, row = O.sgolay2d(z, window, order, "both")
+        assert _rel(col, g[f"col_{window}_{order}"]) < 1e-13 and _rel(row, g[f"row_{window}_{order}"]) < 1e-13
+
+
+@pytest.mark.gpu
+def test_gpu_sgolay2d_golden():
+    from pydfcsr_b200 import ops
+    z, g = _sgolay_cases()
+    dz = _up(z)
+    for window, order in g["cases"]:
+        window, order = int(window), int(order)
+        assert _rel(ops.sgolay2d(dz, window, order).cpu().numpy(), g[f"smooth_{window}_{order}"]) < 1e-13
+        col, row = ops.sgolay2d(dz, window, order, "both")
+        assert _rel(col.cpu().numpy(), g[f"col_{window}_{order}"]) < 1e-13
+        assert _rel(row.cpu().numpy(), g[f"row_{window}_{order}"]) < 1e-13
+        assert _rel(ops.sgolay2d(dz, window, order, "row").cpu().numpy(), g[f"row_{window}_{order}"]) < 1e-13

@@ -258,3 +258,37 @@ def test_wake_fp32_storage_mode(dev, tilt):
     # pack/unpack round trip of fp32 voxels equals a float32 cast of the fields
     back = ops.history_unpack(hist32.ring[5], st.shape[1], st.shape[2]).cpu().numpy()
     assert np.array_equal(back[0], st.data["density"][0].astype(np.float32).astype(np.float64))
+
+
+@pytest.mark.parametrize("shape,window,order", [((100, 100), 5, 2), ((300, 300), 9, 1), ((64, 512), 9, 2), ((33, 65), 25, 2),
+                                                ((97, 31), 7, 3), ((3, 3), 3, 1), ((40, 40), 1, 0)])
+def test_sgolay2d(dev, shape, window, order):
+    """2-D Savitzky-Golay operator (SGolay_filter.py:3-81) against the oracle: every border region of the
+    extension, tiles that are not multiples of 32, the largest window."""
+    from pydfcsr_b200 import ops
+    rng = np.random.default_rng(window + shape[0])
+    z = rng.normal(size=shape) + np.linspace(0, 3, shape[1])[None, :] ** 2 - np.linspace(-1, 2, shape[0])[:, None]
+    dz = _up(z, dev)
+    assert _rel(ops.sgolay2d(dz, window, order).cpu().numpy(), O.sgolay2d(z, window, order)) < 1e-13
+    if order >= 1:
+        col, row = ops.sgolay2d(dz, window, order, "both")
+        ref = O.sgolay2d(z, window, order, "both")
+        assert _rel(col.cpu().numpy(), ref[0]) < 1e-13 and _rel(row.cpu().numpy(), ref[1]) < 1e-13
+        # a plane a*i + b*j is reproduced exactly by the fit: derivative stencils return its slopes
+        i, j = np.meshgrid(np.arange(shape[0], dtype=float), np.arange(shape[1], dtype=float), indexing="ij")
+        col, row = ops.sgolay2d(_up(0.25 * i - 1.5 * j, dev), window, order, "both")
+        h = window // 2
+        inner = (slice(h, shape[0] - h), slice(h, shape[1] - h))
+        if shape[0] > 2 * h:
+            assert np.allclose(col.cpu().numpy()[inner], 0.25, atol=1e-11) and np.allclose(row.cpu().numpy()[inner], -1.5, atol=1e-11)
+
+
+def test_sgolay2d_errors(dev):
+    from pydfcsr_b200 import _lib, ops
+    z = _up(np.zeros((8, 8)), dev)
+    with pytest.raises(_lib.DfcsrError):
+        ops.sgolay2d(z, 9, 1)                   # array smaller than the window
+    with pytest.raises(ValueError):
+        ops.sgolay2d(z, 4, 1)
+    with pytest.raises(ValueError):
+        ops.sgolay2d(z, 5, 1, "diag")

@@ -140,3 +140,26 @@ def test_product_lattice_matches_reference(ref, tmp_path):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
     assert a.delta_x == b.delta_x and a.total_steps == b.total_steps and a.step_size == b.step_size
     assert np.array_equal(a.CSR_steps_index, b.CSR_steps_index)
+
+
+@pytest.mark.parametrize("shape,window,order", [((40, 50), 5, 2), ((64, 96), 9, 1), ((30, 30), 7, 3), ((11, 13), 11, 4),
+                                                ((100, 100), 15, 2), ((9, 9), 3, 1), ((33, 65), 25, 2)])
+def test_sgolay2d_matches_reference(ref, shape, window, order):
+    """SGolay_filter.py:3-81 (border extension, kernel order and signs, 'valid' convolution)."""
+    from pyDFCSR_2D.SGolay_filter import sgolay2d
+    from pydfcsr_b200 import ops
+    rng = np.random.default_rng(window)
+    z = rng.normal(size=shape) + np.linspace(0, 3, shape[1])[None, :] ** 2 - np.linspace(-1, 2, shape[0])[:, None]
+    half = window // 2
+    import scipy.signal  # noqa: F401  (the reference file uses scipy.signal without importing the submodule)
+    assert np.array_equal(O.sgolay2d_pad(z, half)[half:-half, half:-half], z)
+    for d in (None, "col", "row"):
+        assert _rel(O.sgolay2d(z, window, order, d), sgolay2d(z, window, order, d)) < 5e-14
+    both_o, both_r = O.sgolay2d(z, window, order, "both"), sgolay2d(z, window, order, "both")
+    assert _rel(both_o[0], both_r[0]) < 5e-14 and _rel(both_o[1], both_r[1]) < 5e-14
+    # the product's host-side kernels are the oracle's
+    assert np.allclose(ops.sgolay2d_kernels(window, order), O.sgolay2d_kernels(window, order), rtol=0, atol=1e-15)
+    for bad in ((4, 1), (3, 4)):
+        for fn in (lambda: sgolay2d(z, *bad), lambda: O.sgolay2d(z, *bad), lambda: ops.sgolay2d_kernels(*bad)):
+            with pytest.raises(ValueError):
+                fn()
