@@ -33,11 +33,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building libdfcsr_b200.so")
     if verbose:
         sys.stderr.write(res.stderr)
-    # measurement helper (not part of the library): L1 load-bandwidth probe used by bench.py
-    probe_src = os.path.join(HERE, "..", "tools", "l1_probe.cu")
-    if os.path.exists(probe_src):
-        subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-o",
-                        os.path.join(HERE, "l1_probe"), probe_src], capture_output=True, text=True)
+    # measurement helpers (not part of the library): the L1 load-bandwidth probe used by bench.py and the
+    # shared-memory atomic probe behind the deposit design
+    for probe in ("l1_probe", "atoms_probe"):
+        probe_src = os.path.join(HERE, "..", "tools", probe + ".cu")
+        if os.path.exists(probe_src):
+            subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-o",
+                            os.path.join(HERE, probe), probe_src], capture_output=True, text=True)
     return LIB
 
 
