@@ -50,7 +50,7 @@ def build(name):
            "CSR_integration": integ,
            "CSR_computation": dict(compute_CSR=1, apply_CSR=0, transverse_on=1, write_beam=None, write_wakes=False,
                                    workdir="/tmp/dfcsr_cfg", xbins=mesh[0], zbins=mesh[1], xlim=5, zlim=5)}
-    return CSR2D(inp, parallel=False, verbose=False), stop
+    return CSR2D(inp, parallel=False, verbose=False, precision=os.environ.get("DFCSR_PRECISION", "fp64")), stop
 
 
 def oracle_points(csr, picks):
