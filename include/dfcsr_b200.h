@@ -123,6 +123,15 @@ int64_t dfcsr_beam_stats_workspace(void);
 int dfcsr_beam_stats(const double* d_x, const double* d_z, const double* d_pz, int64_t n,
                      double* d_stats, void* d_workspace, void* stream);
 
+/* ---- 6 x 6 phase-space covariance (twiss.py:2-71: np.cov([x, px, pz]) and np.cov([y, py, pz]) per step,
+ * CSR.py:837-859) -- one read of the six coordinate arrays, deterministic reduction.
+ * d_out[27]: means of (x, px, y, py, z, pz), then the upper triangle (i <= j, row-major) of the covariance
+ * with np.cov's 1/(n-1) normalisation.  d_workspace: dfcsr_beam_cov_workspace() bytes, zero-initialised once. */
+int64_t dfcsr_beam_cov_workspace(void);
+int dfcsr_beam_cov(const double* d_x, const double* d_px, const double* d_y, const double* d_py,
+                   const double* d_z, const double* d_pz, int64_t n, double* d_out, void* d_workspace,
+                   void* stream);
+
 /* ---- A1 / K1 particle deposition (deposit.py:42-87, called at deposit.py:172,178) --------------
  * One pass deposits both weights (w = 1 and w = px) with CIC on an (nx, nz) grid whose bin spacing
  * is (end - start) / n.  d_count / d_vxsum (nx*nz doubles each) are zeroed by the call.

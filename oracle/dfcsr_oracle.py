@@ -735,3 +735,22 @@ def apply_kick(x, z, px, pz, de_dct, x_kick, xrange_t, zrange, step_size, init_e
     if transverse_on:
         px_new = px + interp_bilinear_points(step_size * x_kick * 1e6 / init_energy, xrange_t, zrange, x_t, z, 0.0)
     return px_new, pz_new
+
+
+# --------------------------------------------------------------------------------------------
+# (f)2  Twiss / dispersion statistics logged every step (twiss.py:2-71, CSR.py:837-859)
+# --------------------------------------------------------------------------------------------
+def twiss_from_coords(coords, p0c, mc2):
+    """Per plane: the 3x3 sample covariance (np.cov, ddof = 1) of (q, p, delta), dispersion removed,
+    then alpha, beta, gamma, emittance, eta, eta' and the normalised emittance (twiss.py:29-71)."""
+    x, px, y, py, _z, pz = (np.asarray(c, dtype=np.float64) for c in coords)
+    out = {}
+    for plane, (q, p) in (("x", (x, px)), ("y", (y, py))):
+        s = np.cov(np.stack([q, p, pz]))
+        d2, qd, pd = s[2, 2], s[0, 2], s[1, 2]
+        e_beta, e_gamma, e_alpha = s[0, 0] - qd * qd / d2, s[1, 1] - pd * pd / d2, -s[0, 1] + qd * pd / d2
+        emit = math.sqrt(e_beta * e_gamma - e_alpha * e_alpha)
+        vals = {"alpha": e_alpha / emit, "beta": e_beta / emit, "gamma": e_gamma / emit, "emit": emit,
+                "eta": qd / d2, "etap": pd / d2, "norm_emit": emit * p0c / mc2}
+        out.update({f"{k}_{plane}": v for k, v in vals.items()})
+    return out

@@ -4,7 +4,7 @@ properties read by the hot path (``_sigma_x, _sigma_z, _slope, _mean_x, _mean_z,
 
 Particles are six CUDA float64 tensors (Bmad-X order x, px, y, py, z, pz); they are uploaded once
 and stay in HBM across tracking, deposition and kick application.  All O(Np) statistics come from
-one call of the device reduction kernels per state change (``ops.beam_stats``), not from numpy.
+the device reduction kernels (``ops.beam_stats`` per state change, ``ops.beam_cov`` for Twiss), not from numpy.
 """
 from __future__ import annotations
 
@@ -149,10 +149,12 @@ class Beam:
 
     @property
     def twiss(self):
-        """Twiss/dispersion from the 3x3 covariances (twiss.py:2-71), computed with torch on device."""
+        """Twiss/dispersion from the 3x3 covariances of (x, px, pz) and (y, py, pz) (twiss.py:2-71); the 6x6
+        covariance comes from one device reduction (ops.beam_cov)."""
+        _, cov6 = ops.beam_cov(self.coords)
         out = {}
-        for plane, (q, p) in (("x", (self.x, self.px)), ("y", (self.y, self.py))):
-            cov = torch.cov(torch.stack([q, p, self.pz])).cpu().numpy()
+        for plane, idx in (("x", (0, 1, 5)), ("y", (2, 3, 5))):
+            cov = cov6[np.ix_(idx, idx)]
             d2, xd, pd = cov[2, 2], cov[0, 2], cov[1, 2]
             eb, eg, ea = cov[0, 0] - xd ** 2 / d2, cov[1, 1] - pd ** 2 / d2, -cov[0, 1] + xd * pd / d2
             emit = np.sqrt(eb * eg - ea ** 2)

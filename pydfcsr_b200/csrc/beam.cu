@@ -22,10 +22,10 @@ struct StatWorkspace {
     unsigned int ticket[4];   // must be zero before the first call; every pass leaves its ticket at zero
 };
 
-template <int NV>
-__device__ __forceinline__ bool block_reduce_publish(double (&v)[NV], double (*partial)[kStatVals],
+template <int NV, int kStride = kStatVals>
+__device__ __forceinline__ bool block_reduce_publish(double (&v)[NV], double (*partial)[kStride],
                                                      unsigned int* ticket, double (&total)[NV]) {
-    __shared__ double sm[kStatThreads / 32][kStatVals];
+    __shared__ double sm[kStatThreads / 32][NV];
     __shared__ bool last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -155,6 +155,53 @@ stats_residuals(const double* __restrict__ x, const double* __restrict__ z, long
     }
 }
 
+// ---- 6 x 6 covariance of the phase-space coordinates (Twiss / dispersion statistics, twiss.py:2-71) ------
+// One read of the six coordinate arrays: sums and upper-triangle products about the first particle, reduced in
+// fixed order like the passes above.  out[0..5] = means, out[6..26] = covariance (i <= j, row-major over the
+// upper triangle) with np.cov's normalisation 1/(n-1).
+constexpr int kCovVals = 27;
+
+struct CovWorkspace {
+    double partial[kStatBlocks][kCovVals];
+    unsigned int ticket[4];
+};
+
+struct SixPtr {
+    const double* q[6];
+};
+
+__global__ void __launch_bounds__(kStatThreads)
+cov6_kernel(SixPtr c, long long n, double* __restrict__ out, CovWorkspace* ws) {
+    double o[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) o[a] = c.q[a][0];
+    double v[kCovVals];
+#pragma unroll
+    for (int k = 0; k < kCovVals; ++k) v[k] = 0.0;
+    for (long long i = (long long)blockIdx.x * kStatThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kStatThreads) {
+        double d[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) d[a] = c.q[a][i] - o[a];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            v[a] += d[a];
+#pragma unroll
+            for (int b = a; b < 6; ++b) {
+                const int k = 6 + a * 6 - (a * (a - 1)) / 2 + (b - a);      // upper triangle, row-major
+                v[k] = fma(d[a], d[b], v[k]);
+            }
+        }
+    }
+    double tot[kCovVals];
+    if (block_reduce_publish<kCovVals, kCovVals>(v, ws->partial, &ws->ticket[0], tot)) {
+        const double inv_n = 1.0 / (double)n, inv_n1 = 1.0 / (double)(n - 1);
+        for (int a = 0; a < 6; ++a) out[a] = o[a] + tot[a] * inv_n;
+        int k = 6;
+        for (int a = 0; a < 6; ++a)
+            for (int b = a; b < 6; ++b, ++k) out[k] = (tot[k] - tot[a] * tot[b] * inv_n) * inv_n1;
+    }
+}
+
 // ---- K5 ---------------------------------------------------------------------------------------
 struct Cell1 {
     int i;
@@ -207,6 +254,23 @@ apply_kick_kernel(const double* __restrict__ x, const double* __restrict__ z, do
 using namespace dfcsr;
 
 extern "C" int64_t dfcsr_beam_stats_workspace(void) { return (int64_t)sizeof(StatWorkspace); }
+
+extern "C" int64_t dfcsr_beam_cov_workspace(void) { return (int64_t)sizeof(CovWorkspace); }
+
+extern "C" int dfcsr_beam_cov(const double* d_x, const double* d_px, const double* d_y, const double* d_py,
+                              const double* d_z, const double* d_pz, int64_t n, double* d_out, void* d_workspace,
+                              void* stream) {
+    DFCSR_REQUIRE(d_x && d_px && d_y && d_py && d_z && d_pz && d_out && d_workspace, "null pointer");
+    DFCSR_REQUIRE(n >= 2, "need at least two particles");
+    SixPtr c;
+    c.q[0] = d_x; c.q[1] = d_px; c.q[2] = d_y; c.q[3] = d_py; c.q[4] = d_z; c.q[5] = d_pz;
+    long long want = (n + kStatThreads - 1) / kStatThreads;
+    unsigned blocks = (unsigned)(want < kStatBlocks ? want : kStatBlocks);
+    cov6_kernel<<<blocks, kStatThreads, 0, as_stream(stream)>>>(c, n, d_out, static_cast<CovWorkspace*>(d_workspace));
+    count_launch(1);
+    DFCSR_CUDA_OK(cudaGetLastError());
+    return DFCSR_OK;
+}
 
 extern "C" int dfcsr_beam_stats(const double* d_x, const double* d_z, const double* d_pz, int64_t n,
                                 double* d_stats, void* d_workspace, void* stream) {

@@ -59,6 +59,28 @@ def beam_stats(x: torch.Tensor, z: torch.Tensor, pz: torch.Tensor | None = None)
     return h_stats.numpy().copy()
 
 
+_cov_ws: dict = {}
+
+
+def beam_cov(coords) -> tuple[np.ndarray, np.ndarray]:
+    """(means[6], cov[6, 6]) of the six coordinate tensors (x, px, y, py, z, pz); np.cov normalisation (ddof = 1).
+    One device pass + 27 doubles to the host.  Synchronises."""
+    dev = coords[0].device
+    if dev not in _cov_ws:
+        _cov_ws[dev] = (torch.zeros(lib.dfcsr_beam_cov_workspace(), dtype=torch.uint8, device=dev),
+                        torch.zeros(27, dtype=F64, device=dev), torch.zeros(27, dtype=F64).pin_memory())
+    ws, d_out, h_out = _cov_ws[dev]
+    ptrs = [_ptr(_f64(c, "coords")) for c in coords]
+    check(lib.dfcsr_beam_cov(*ptrs, coords[0].numel(), _ptr(d_out), _ptr(ws), _stream()), "dfcsr_beam_cov")
+    h_out.copy_(d_out, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    flat = h_out.numpy()
+    cov = np.zeros((6, 6))
+    cov[np.triu_indices(6)] = flat[6:]
+    cov = cov + np.triu(cov, 1).T
+    return flat[:6].copy(), cov
+
+
 # ---------------------------------------------------------------------------------------------
 # K1 deposit
 # ---------------------------------------------------------------------------------------------

@@ -292,3 +292,26 @@ def test_sgolay2d_errors(dev):
         ops.sgolay2d(z, 4, 1)
     with pytest.raises(ValueError):
         ops.sgolay2d(z, 5, 1, "diag")
+
+
+def test_beam_cov_and_twiss(dev):
+    """6x6 covariance in one device pass (np.cov normalisation) and the Twiss statistics built on it
+    (twiss.py:2-71), for a bunch far from the origin (the shifted sums must not lose the small variances)."""
+    import torch
+    from pydfcsr_b200 import Beam, ops, synth
+    b = synth.gaussian_bunch(400_003, seed=13, tilt=1.2)
+    b[0] += 0.02 * b[5] + 3.0e-3             # dispersion and a 50-sigma offset
+    b[4] += 1.0e-2
+    coords = [_up(c, dev) for c in b]
+    mean, cov = ops.beam_cov(coords)
+    ref_cov = np.cov(b)
+    scale = np.sqrt(np.outer(np.diag(ref_cov), np.diag(ref_cov)))
+    assert np.max(np.abs(cov - ref_cov) / scale) < 1e-10
+    assert np.max(np.abs(mean - b.mean(axis=1)) / np.sqrt(np.diag(ref_cov))) < 1e-10
+    m2, c2 = ops.beam_cov(coords)
+    assert np.array_equal(cov, c2) and np.array_equal(mean, m2)            # deterministic reduction
+    beam = Beam({"style": "array", "coords": torch.stack(coords), "charge": 1e-9, "energy": 5.0e9}, device=dev)
+    want = O.twiss_from_coords(b, 5.0e9, 0.51099895e6)
+    got = beam.twiss
+    for k, v in want.items():
+        assert abs(got[k] - v) <= 1e-8 * abs(v), (k, got[k], v)

@@ -163,3 +163,18 @@ def test_sgolay2d_matches_reference(ref, shape, window, order):
         for fn in (lambda: sgolay2d(z, *bad), lambda: O.sgolay2d(z, *bad), lambda: ops.sgolay2d_kernels(*bad)):
             with pytest.raises(ValueError):
                 fn()
+
+
+def test_twiss_matches_reference(ref):
+    """twiss.py:2-71 on a chirped, dispersed bunch."""
+    from types import SimpleNamespace
+    from pyDFCSR_2D.twiss import twiss_from_bmadx_particles
+    from pydfcsr_b200 import synth
+    b = synth.gaussian_bunch(50_000, seed=9, tilt=0.7)
+    b[0] += 0.02 * b[5]                       # some dispersion
+    p = SimpleNamespace(x=b[0], px=b[1], y=b[2], py=b[3], z=b[4], pz=b[5], p0c=5.0e9, mc2=0.51099895e6)
+    want = twiss_from_bmadx_particles(p)
+    got = O.twiss_from_coords(b, 5.0e9, 0.51099895e6)
+    assert set(got) == set(want)
+    for k in want:
+        assert abs(got[k] - want[k]) <= 1e-12 * abs(want[k]), k
