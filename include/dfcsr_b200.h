@@ -214,6 +214,13 @@ int dfcsr_apply_kick(const double* d_x, const double* d_z, double* d_px, double*
                      const double* d_dE, const double* d_kick, dfcsr_axis x_axis, dfcsr_axis z_axis,
                      double step_size, double init_energy, int32_t transverse_on, void* stream);
 
+/* ---- linear transfer map -------------------------------------------------------
+ * v <- M v for every particle, v = (x, px, y, py, z, pz), in place.  h_matrix: 36 HOST doubles, row-major.
+ * First-order stand-in for Bmad-X track_element (beams.py:101-102) when that package is absent: drift,
+ * sector bend with pole-face rotations, thick quadrupole (pydfcsr_b200/tracking.py builds the matrices). */
+int dfcsr_track_linear(double* d_x, double* d_px, double* d_y, double* d_py, double* d_z, double* d_pz,
+                       int64_t n, const double* h_matrix, void* stream);
+
 /* ---- 2-D Savitzky-Golay operator (SGolay_filter.py:3-81) ---------------------
  * sgolay2d(z, window_size, order, derivative): d_z (rows x cols, row-major) is extended by window/2
  * samples per side with the reference's reflection rule (SGolay_filter.py:36-65) and convolved

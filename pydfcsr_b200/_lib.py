@@ -78,6 +78,7 @@ SIGNATURES = {
     "dfcsr_wake_point_debug": (C.c_int, [C.POINTER(History), C.POINTER(Lattice), C.POINTER(WakeParams),
                                          _D, _D, _P, _P, _L, _P, _P, _P]),
     "dfcsr_apply_kick": (C.c_int, [_P, _P, _P, _P, _L, _D, _D, _P, _P, Axis, Axis, _D, _D, _I, _P]),
+    "dfcsr_track_linear": (C.c_int, [_P, _P, _P, _P, _P, _P, _L, C.POINTER(C.c_double), _P]),
     "dfcsr_sgolay2d": (C.c_int, [_P, _I, _I, _I, _P, _I, _P, _P]),
 }
 

@@ -249,9 +249,47 @@ apply_kick_kernel(const double* __restrict__ x, const double* __restrict__ z, do
     }
 }
 
+// ---- linear transfer map (first-order stand-in for track_element, beams.py:101-102) ----
+// v <- M v for every particle, in place: 96 B / particle, one pass instead of a dozen elementwise launches.
+struct Map6 {
+    double m[36];
+};
+
+__global__ void __launch_bounds__(256)
+track_linear_kernel(double* __restrict__ x, double* __restrict__ px, double* __restrict__ y, double* __restrict__ py,
+                    double* __restrict__ z, double* __restrict__ pz, long long n, Map6 M) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        const double v[6] = {x[p], px[p], y[p], py[p], z[p], pz[p]};
+        double o[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            double a = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) a = fma(M.m[6 * r + c], v[c], a);
+            o[r] = a;
+        }
+        x[p] = o[0]; px[p] = o[1]; y[p] = o[2]; py[p] = o[3]; z[p] = o[4]; pz[p] = o[5];
+    }
+}
+
 }  // namespace dfcsr
 
 using namespace dfcsr;
+
+extern "C" int dfcsr_track_linear(double* d_x, double* d_px, double* d_y, double* d_py, double* d_z, double* d_pz,
+                                  int64_t n, const double* h_matrix, void* stream) {
+    DFCSR_REQUIRE(h_matrix && n >= 0, "null matrix or negative count");
+    if (n == 0) return DFCSR_OK;
+    DFCSR_REQUIRE(d_x && d_px && d_y && d_py && d_z && d_pz, "null pointer");
+    Map6 M;
+    for (int k = 0; k < 36; ++k) M.m[k] = h_matrix[k];
+    long long want = (n + 255) / 256;
+    unsigned blocks = (unsigned)(want < 148LL * 64 ? want : 148LL * 64);
+    track_linear_kernel<<<blocks, 256, 0, as_stream(stream)>>>(d_x, d_px, d_y, d_py, d_z, d_pz, n, M);
+    count_launch(1);
+    DFCSR_CUDA_OK(cudaGetLastError());
+    return DFCSR_OK;
+}
 
 extern "C" int64_t dfcsr_beam_stats_workspace(void) { return (int64_t)sizeof(StatWorkspace); }
 

@@ -370,3 +370,14 @@ def apply_kick(x, z, px, pz, slope, intercept, dE, kick, x_axis: Axis, z_axis: A
                                x.numel(), float(slope), float(intercept), _ptr(_f64(dE, "dE")), _ptr(_f64(kick, "kick")),
                                x_axis, z_axis, float(step_size), float(init_energy), int(bool(transverse_on)),
                                _stream()), "dfcsr_apply_kick")
+
+
+# ---------------------------------------------------------------------------------------------
+# linear transfer map (tracking stand-in)
+# ---------------------------------------------------------------------------------------------
+def track_linear(coords, matrix) -> None:
+    """v <- M v in place for the six coordinate tensors (x, px, y, py, z, pz); `matrix` is a host (6, 6) array."""
+    m = np.ascontiguousarray(matrix, dtype=np.float64).reshape(36)
+    ptrs = [_ptr(_f64(c, "coords")) for c in coords]
+    check(lib.dfcsr_track_linear(*ptrs, coords[0].numel(), m.ctypes.data_as(C.POINTER(C.c_double)), _stream()),
+          "dfcsr_track_linear")

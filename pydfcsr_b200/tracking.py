@@ -59,8 +59,26 @@ def _edge(x, px, y, py, g, e):
     return px + k * x, py - k * y
 
 
+def linear_matrix(element):
+    """The 6 x 6 transfer matrix of `element`: the maps below applied to the unit vectors."""
+    import numpy as np
+    cols = _apply_map(tuple(np.eye(6)), element)          # row k of eye = coordinate k of the six unit particles
+    return np.stack([np.asarray(c, dtype=np.float64) for c in cols])
+
+
 def track_linear(coords, element):
-    """coords: sequence (x, px, y, py, z, pz) of equally shaped arrays; returns the same."""
+    """coords: sequence (x, px, y, py, z, pz) of equally shaped arrays; returns the same.
+    CUDA tensors are transformed in place by one kernel launch (ops.track_linear); host arrays by the
+    expressions in `_apply_map`."""
+    if getattr(coords[0], "is_cuda", False):
+        from . import ops
+        coords = tuple(c if c.is_contiguous() else c.contiguous() for c in coords)
+        ops.track_linear(coords, linear_matrix(element))
+        return coords
+    return _apply_map(coords, element)
+
+
+def _apply_map(coords, element):
     x, px, y, py, z, pz = coords
     L = element.L
     if isinstance(element, SBend) and element.G != 0.0:

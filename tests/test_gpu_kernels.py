@@ -315,3 +315,23 @@ def test_beam_cov_and_twiss(dev):
     got = beam.twiss
     for k, v in want.items():
         assert abs(got[k] - v) <= 1e-8 * abs(v), (k, got[k], v)
+
+
+def test_track_linear_kernel_matches_host_maps(dev):
+    """The device transfer-map kernel against the host expressions of pydfcsr_b200/tracking.py for every
+    element type of the stand-in tracker (drift, bend with edges, both quadrupole signs)."""
+    from pydfcsr_b200 import synth, tracking
+    b = synth.gaussian_bunch(50_001, seed=17, tilt=0.3)
+    elements = [tracking.Drift(0.37), tracking.SBend(L=0.5002, G=0.0483 / 0.5002, E1=0.0, E2=0.0483),
+                tracking.SBend(L=0.1, G=-0.0483 / 0.5002, E1=-0.0483, E2=0.0, FRINGE_AT="entrance_end"),
+                tracking.Quadrupole(L=0.2, K1=1.7), tracking.Quadrupole(L=0.2, K1=-0.9), tracking.Sextupole(L=0.1, K2=3.0)]
+    for el in elements:
+        want = tracking.track_linear(tuple(b), el)
+        dev_coords = tuple(_up(c, dev) for c in b)
+        got = tracking.track_linear(dev_coords, el)
+        assert all(g.data_ptr() == d.data_ptr() for g, d in zip(got, dev_coords))          # in place
+        for k in range(6):
+            scale = max(np.max(np.abs(want[k])), 1e-300)
+            assert np.max(np.abs(got[k].cpu().numpy() - want[k])) <= 1e-14 * scale, (type(el).__name__, k)
+        m = tracking.linear_matrix(el)
+        assert abs(np.linalg.det(m) - 1.0) < 1e-12                                           # symplectic maps
