@@ -232,6 +232,14 @@ int dfcsr_track_linear(double* d_x, double* d_px, double* d_y, double* d_py, dou
 int dfcsr_sgolay2d(const double* d_z, int32_t rows, int32_t cols, int32_t window,
                    const double* d_kernels, int32_t n_kernels, double* d_out, void* stream);
 
+/* ---- diagnostics -------------------------------------------------------------------------------------
+ * K4 derives r = sqrt(r2) and 1/r from ONE reciprocal-square-root seed (wake.cu: sqrt_pair_fast); the
+ * retarded time t - r must be the correctly rounded square root np.sqrt returns (CSR.py:647).  This entry
+ * compares that routine bit for bit with the CUDA library's sqrt.rn.f64 and rsqrt on n pseudo-random
+ * doubles with all 52 mantissa bits random and binary exponents uniform in [lo_exp, hi_exp):
+ * h_mismatch[0] = sqrt results that differ, h_mismatch[1] = reciprocal results that differ.  Synchronises. */
+int dfcsr_selftest_sqrt(int64_t n, uint64_t seed, double lo_exp, double hi_exp, uint64_t* h_mismatch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,7 @@ SIGNATURES = {
     "dfcsr_apply_kick": (C.c_int, [_P, _P, _P, _P, _L, _D, _D, _P, _P, Axis, Axis, _D, _D, _I, _P]),
     "dfcsr_track_linear": (C.c_int, [_P, _P, _P, _P, _P, _P, _L, C.POINTER(C.c_double), _P]),
     "dfcsr_sgolay2d": (C.c_int, [_P, _I, _I, _I, _P, _I, _P, _P]),
+    "dfcsr_selftest_sqrt": (C.c_int, [_L, C.c_uint64, _D, _D, C.POINTER(C.c_uint64), _P]),
 }
 
 

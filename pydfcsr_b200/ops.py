@@ -381,3 +381,14 @@ def track_linear(coords, matrix) -> None:
     ptrs = [_ptr(_f64(c, "coords")) for c in coords]
     check(lib.dfcsr_track_linear(*ptrs, coords[0].numel(), m.ctypes.data_as(C.POINTER(C.c_double)), _stream()),
           "dfcsr_track_linear")
+
+
+# ---------------------------------------------------------------------------------------------
+# diagnostics
+# ---------------------------------------------------------------------------------------------
+def selftest_sqrt(n: int, seed: int = 0, lo_exp: float = -60.0, hi_exp: float = 8.0):
+    """Bitwise comparison of K4's fused sqrt / reciprocal-sqrt with the CUDA library's sqrt.rn.f64 and rsqrt on
+    n pseudo-random doubles (binary exponents in [lo_exp, hi_exp)): returns (sqrt mismatches, rsqrt mismatches)."""
+    out = (C.c_uint64 * 2)(0, 0)
+    check(lib.dfcsr_selftest_sqrt(int(n), int(seed), float(lo_exp), float(hi_exp), out, _stream()), "dfcsr_selftest_sqrt")
+    return int(out[0]), int(out[1])

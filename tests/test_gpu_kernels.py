@@ -335,3 +335,45 @@ def test_track_linear_kernel_matches_host_maps(dev):
             assert np.max(np.abs(got[k].cpu().numpy() - want[k])) <= 1e-14 * scale, (type(el).__name__, k)
         m = tracking.linear_matrix(el)
         assert abs(np.linalg.det(m) - 1.0) < 1e-12                                           # symplectic maps
+
+
+# K4 kernel variants (developer knob DFCSR_WAKE_CFG, read per launch): every shipped variant must meet the same
+# gate as the default.  1 = round-1 s'-lane kernel, 10 = x'-lane register-cached kernel, 20 = trimmed s'-lane
+# kernel, 21/25 = two x' nodes per lane (CTA shapes 2x256 / 2x192 threads per SM).
+@pytest.mark.parametrize("cfg", [1, 10, 20, 21, 25])
+@pytest.mark.parametrize("tilt", [0.0, 2.5])
+def test_wake_kernel_variants_match_oracle(dev, monkeypatch, cfg, tilt):
+    from pydfcsr_b200 import ops
+    monkeypatch.setenv("DFCSR_WAKE_CFG", str(cfg))
+    sc = scenario.chicane_entry(tilt=tilt)
+    nx, nz = 50, 45           # odd x' count in the half-width rectangles: the last pair of a region is half empty
+    hist, dlat, wp, osc = _device_problem(sc, dev, nx, nz)
+    x, z = sc["coords"][0], sc["coords"][4]
+    s = sc["scalars"]
+    xm, zm, _, _ = O.observation_mesh(x, z, s["slope"], s["sigma_z"], s["mean_z"], 3, 3, 5, 7)
+    import torch
+    cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+    de, kick = ops.wake_mesh(hist, dlat, wp, _up(xm, dev), _up(zm, dev), counters=cnt)
+    ref_de, ref_kick = O.wake_mesh(xm, zm, osc, sc["lattice"], sc["stack"])
+    assert _rel(de.cpu().numpy(), ref_de) < TOL
+    assert _rel(kick.cpu().numpy(), ref_kick) < TOL
+    n_in, n_all = (int(v) for v in cnt.cpu())
+    assert n_all == xm.size * (4 if abs(tilt) <= 1 else 5) * nx * nz and 0 < n_in < n_all
+    # the in-grid sample count is a property of the quadrature, not of the kernel variant
+    monkeypatch.setenv("DFCSR_WAKE_CFG", "1")
+    cnt1 = torch.zeros(2, dtype=torch.int64, device=dev)
+    ops.wake_mesh(hist, dlat, wp, _up(xm, dev), _up(zm, dev), counters=cnt1)
+    assert int(cnt1[0]) == n_in
+    # run-to-run bitwise reproducible
+    monkeypatch.setenv("DFCSR_WAKE_CFG", str(cfg))
+    de2, kick2 = ops.wake_mesh(hist, dlat, wp, _up(xm, dev), _up(zm, dev))
+    assert torch.equal(de, de2) and torch.equal(kick, kick2)
+
+
+def test_fused_sqrt_is_bitwise_the_library_sqrt(dev):
+    """t_ret = t - r must use the correctly rounded square root: the fused sqrt/rsqrt of the
+    trimmed K4 kernels is compared bit for bit with sqrt.rn.f64 / rsqrt on 6e8 random arguments."""
+    from pydfcsr_b200 import ops
+    for seed, (lo, hi) in enumerate([(-60.0, 8.0), (-2.0, 2.0), (-1000.0, 1000.0)]):
+        bad_r, bad_y = ops.selftest_sqrt(200_000_000, seed=seed + 1, lo_exp=lo, hi_exp=hi)
+        assert bad_r == 0 and bad_y == 0, (lo, hi, bad_r, bad_y)

@@ -1,0 +1,51 @@
+"""Developer tool: time every K4 kernel variant (DFCSR_WAKE_CFG, read per launch by the library) on the bench
+workload in ONE process and compare each variant's wake grids with the round-1 kernel (cfg 1).
+
+    python tools/k4_variants.py [reps] [cfg ...]        DFCSR_TILT=2.5 adds an x-z tilt (chirp-band quadrature)
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from pydfcsr_b200 import CSR2D  # noqa: E402
+
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+cfgs = [int(a) for a in sys.argv[2:]] or [1, 10, 20, 21, 25]
+wl = bench.WORKLOAD
+inp = bench._input_dict(wl)
+tilt = os.environ.get("DFCSR_TILT")
+if tilt:
+    inp["input_beam"]["tilt"] = float(tilt)
+csr = CSR2D(inp, parallel=False, verbose=False, precision=os.environ.get("DFCSR_PRECISION", "fp64"))
+csr.run(stop_time=wl["position"] - 0.05)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=csr.device)
+print(f"# K4 variants on the bench workload, tilt={tilt or 0}, precision={os.environ.get('DFCSR_PRECISION', 'fp64')}, "
+      f"history {tuple(csr.DF_tracker.data_shape) if hasattr(csr.DF_tracker, 'data_shape') else ''}, "
+      f"slope {float(csr.beam._slope[0]):.3f}")
+ref = None
+for cfg in cfgs:
+    os.environ["DFCSR_WAKE_CFG"] = str(cfg)
+    for _ in range(3):
+        csr.calculate_2D_CSR()
+    dE, kick = csr.dE_dct.clone(), csr.x_kick.clone()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        csr.calculate_2D_CSR()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    rep = bool(torch.equal(dE, csr.dE_dct) and torch.equal(kick, csr.x_kick))
+    if ref is None:
+        ref = (dE, kick)
+    e1 = float((dE - ref[0]).abs().max() / ref[0].abs().max())
+    e2 = float((kick - ref[1]).abs().max() / ref[1].abs().max())
+    print(f"cfg {cfg:3d}: median {np.median(ts):7.3f} ms  min {np.min(ts):7.3f} ms  vs cfg {cfgs[0]}: dE {e1:.2e} kick {e2:.2e}  "
+          f"bitwise_repeatable {rep}", flush=True)
