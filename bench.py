@@ -431,14 +431,14 @@ def gpu_arm(args):
                 "d2h_bytes_per_step": int(out_host[0].numel() * 8 * 2 + out_host[2].numel() * 8)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "wake_mesh_kernel (K4)", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "wake_mesh_kernel_p (K4)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                      "k4_ms_per_launch": k4_ms, "k4_share_of_step": k4_ms / ms_step,
                      "in_grid_samples_per_launch": n_in_local, "in_grid_fraction": n_in_local / (n_pts * spp / world),
                      "note": "algorithmic bytes = 320 B per in-grid integrand sample: gather traffic served by L1/L2 "
-                             "(stack footprint << bytes), so frac can exceed 1 against the HBM copy peak; the kernel's "
-                             "real limiter is the fp64 pipe (see DESIGN.md, profiles/)"},
+                             "(stack footprint << bytes), so frac can exceed 1 against the HBM copy peak; what binds is "
+                             "instruction issue with half-rate fp64 plus the L1 load path (see DESIGN.md, profiles/)"},
     }
     if probe:
         l1_peak = max(probe["l1_broadcast_gbs"], probe["l1_contiguous_gbs"])
