@@ -30,6 +30,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_JSON_OUT = sys.stdout
 METRIC = "csr_wake_obs_points_x_integrand_samples_per_s"
 UNIT = "point-samples/s"
 
@@ -229,7 +230,7 @@ def reference_arm(args):
                        "n_particle": wl["n_particle"], "history": list(hist.shape)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # -------------------------------------------------------------------------------------------------
@@ -463,7 +464,7 @@ def gpu_arm(args):
                                           f"only, {cores} fork workers, {sec:.2f} s",
                                 "parity_max_rel_dE": float(np.max(np.abs(g_de - de)) / np.max(np.abs(de))),
                                 "parity_max_rel_kick": float(np.max(np.abs(g_kick - kick)) / np.max(np.abs(kick)))}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def _export_state(csr, trk, O, pristine):
@@ -505,6 +506,11 @@ def main():
     ap.add_argument("--cpu-points-per-core", type=int, default=256, help="mesh points per host core in the cpu_baseline leg")
     ap.add_argument("--ref-points-per-core", type=int, default=256, help="mesh points per host core per step (--impl reference)")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON record; everything the library prints on the way (the reference's
+    # "start reinterpolation" messages, deposit.py:340) goes to stderr
+    global _JSON_OUT
+    _JSON_OUT = sys.stdout
+    sys.stdout = sys.stderr
     if args.impl == "reference":
         args.steps = 3 if args.steps is None else args.steps
         args.warmup = 1 if args.warmup is None else args.warmup

@@ -340,7 +340,7 @@ def test_track_linear_kernel_matches_host_maps(dev):
 # K4 kernel variants (developer knob DFCSR_WAKE_CFG, read per launch): every shipped variant must meet the same
 # gate as the default.  1 = round-1 s'-lane kernel, 10 = x'-lane register-cached kernel, 20 = trimmed s'-lane
 # kernel, 21/25 = two x' nodes per lane (CTA shapes 2x256 / 2x192 threads per SM).
-@pytest.mark.parametrize("cfg", [0, 1, 10, 20, 25, 30])
+@pytest.mark.parametrize("cfg", [0, 1, 10, 20, 25, 30, 40])
 @pytest.mark.parametrize("tilt", [0.0, 2.5])
 def test_wake_kernel_variants_match_oracle(dev, monkeypatch, cfg, tilt):
     from pydfcsr_b200 import ops
