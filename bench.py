@@ -261,7 +261,7 @@ def gpu_arm(args):
     wp = csr._wake_params()
     spp = (4 if abs(wp.slope0) <= 1 else 5) * wp.nx * wp.nz
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    counters = torch.zeros(2, dtype=torch.int64, device=dev)
+    counters = torch.zeros(3, dtype=torch.int64, device=dev)
     csr.wake_counters = counters
     out_host = [torch.empty_like(host[1]).pin_memory(), torch.empty_like(host[5]).pin_memory(),
                 torch.empty((2, csr.CSR_params.xbins, csr.CSR_params.zbins), dtype=torch.float64).pin_memory()]
@@ -374,6 +374,7 @@ def gpu_arm(args):
     launches = _lib.lib.dfcsr_launch_count() - launches0
     k4_ms = float(np.mean([a.elapsed_time(b) for a, b in k4_events]))
     n_in_local = int(counters[0]) / args.steps
+    n_gat_local = int(counters[2]) / args.steps          # in-grid samples whose voxels were actually gathered
     for _ in range(2):
         step_e2e()
     ms_e2e_serial = timed(step_e2e, args.steps)
@@ -403,7 +404,7 @@ def gpu_arm(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     # 5 fields x 8 corners x 8 B per in-grid sample; 4 B in the optional fp32-storage mode
-    k4_bytes = (320.0 if args.precision == "fp64" else 160.0) * n_in_local
+    k4_bytes = (320.0 if args.precision == "fp64" else 160.0) * n_gat_local
     traffic = None                      # DRAM bytes per K4 launch from the committed ncu --set full capture
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "k4_ncu_traffic.json")))
@@ -437,7 +438,9 @@ def gpu_arm(args):
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                      "k4_ms_per_launch": k4_ms, "k4_share_of_step": k4_ms / ms_step,
                      "in_grid_samples_per_launch": n_in_local, "in_grid_fraction": n_in_local / (n_pts * spp / world),
-                     "note": "algorithmic bytes = 320 B per in-grid integrand sample: gather traffic served by L1/L2 "
+                     "gathered_samples_per_launch": n_gat_local,
+                     "note": "algorithmic bytes = 320 B per in-grid integrand sample that is actually gathered (samples whose eight voxels "
+                             "carry no density are skipped via the row-support table and count 0 B): gather traffic served by L1/L2 "
                              "(stack footprint << bytes), so frac can exceed 1 against the HBM copy peak; what binds is "
                              "instruction issue with half-rate fp64 plus the L1 load path (see DESIGN.md, profiles/)"},
     }

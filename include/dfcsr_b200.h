@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DFCSR_ABI_VERSION 1
+#define DFCSR_ABI_VERSION 2
 #define DFCSR_VOXEL_DOUBLES 6   /* fp64 voxel: 48 bytes */
 #define DFCSR_VOXEL_FLOATS 8    /* fp32 voxel: 32 bytes {density, density_x, density_z, vx, vx_x, 0, 0, 0} */
 #define DFCSR_LATTICE_DOUBLES 6
@@ -87,6 +87,12 @@ typedef struct dfcsr_history {
     int32_t format;            /* dfcsr_voxel_format                                 */
     double min_t, min_x, min_z;      /* deposit.py:416-418 (min_x / min_y / min_z there) */
     double delta_t, delta_x, delta_z;/* deposit.py:419-421                               */
+    const int32_t* d_row_support;    /* (cap, X, 2) int32 or NULL: per (slot, transverse row) the hull [z_lo, z_hi] of
+                                        the voxels whose density or density gradient is non-zero (z_lo > z_hi: none),
+                                        written by dfcsr_history_row_support.  Every term of the integrand carries a
+                                        factor rho or grad rho of the retarded point (CSR.py:732-775), so a sample whose
+                                        eight voxels lie outside the hulls contributes exactly 0 and K4 skips it
+                                        without touching the history.  NULL = unknown, nothing is skipped.      */
 } dfcsr_history;
 
 /* reference-orbit tables consumed by the integrand (lattice.py:136-143, CSR.py:619-656) */
@@ -177,6 +183,11 @@ int dfcsr_history_regrid(const double* d_fields, dfcsr_axis src_x, dfcsr_axis sr
                          dfcsr_axis dst_x, dfcsr_axis dst_z, double fill_vx_x, const double* d_fill_vx_x,
                          int32_t format, void* d_slice, void* stream);
 
+/* Row support of one voxel slice (see dfcsr_history.d_row_support): d_support[X][2] = {z_lo, z_hi} per row, the
+ * first and last z index whose density, d(density)/dx or d(density)/dz is not exactly zero (NaN counts as non-zero);
+ * {INT32_MAX, -1} for an all-zero row.  Call it after every dfcsr_history_regrid / dfcsr_history_pack of a slot. */
+int dfcsr_history_row_support(const void* d_slice, int32_t X, int32_t Z, int32_t format, int32_t* d_support, void* stream);
+
 /* field stack (5, X, Z) <-> voxel slice (X, Z, 6): import/export of oracle histories in tests */
 int dfcsr_history_pack(const double* d_fields, int32_t X, int32_t Z, int32_t format, void* d_slice, void* stream);
 int dfcsr_history_unpack(const void* d_slice, int32_t X, int32_t Z, int32_t format, double* d_fields, void* stream);
@@ -184,8 +195,9 @@ int dfcsr_history_unpack(const void* d_slice, int32_t X, int32_t Z, int32_t form
 /* ---- A10-A12 / K4 wake on the observation mesh (CSR.py:397-451, 454-602, 605-782) --------------
  * For k in [0, count): s = t + d_zmesh[first + k], x = d_xmesh[first + k];
  * d_dE[k], d_kick[k] = get_CSR_wake(s, x).  first/count implement the reference's MPI block split
- * (CSR.py:121-125, 434-445).  d_counters (may be NULL): [0] += in-grid integrand samples,
- * [1] += evaluated samples (device-side accounting for the roofline figure). */
+ * (CSR.py:121-125, 434-445).  d_counters (may be NULL, else THREE counters): [0] += in-grid integrand samples,
+ * [1] += samples the reference evaluates, [2] += in-grid samples whose history voxels were actually gathered
+ * (= [0] without d_row_support) -- device-side accounting for the roofline figure. */
 int dfcsr_wake_mesh(const dfcsr_history* hist, const dfcsr_lattice* lat, const dfcsr_wake_params* wp,
                     const double* d_xmesh, const double* d_zmesh, int64_t first, int64_t count,
                     double* d_dE, double* d_kick, unsigned long long* d_counters, void* stream);

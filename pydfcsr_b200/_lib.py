@@ -17,7 +17,7 @@ VOXEL_F64, VOXEL_F32 = 0, 1
 LATTICE_DOUBLES = 6
 STATS_DOUBLES = 16
 DF_SCALARS = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # indices of dfcsr_stat
 (S_MEAN_X, S_MEAN_Z, S_SIGMA_X, S_SIGMA_Z, S_SLOPE, S_INTERCEPT, S_MEAN_XT, S_SIGMA_XT,
@@ -36,7 +36,8 @@ class History(C.Structure):
     _fields_ = [("d_ring", C.c_void_p), ("slice_elems", C.c_int64), ("cap", C.c_int32), ("head", C.c_int32),
                 ("T", C.c_int32), ("X", C.c_int32), ("Z", C.c_int32), ("format", C.c_int32),
                 ("min_t", C.c_double), ("min_x", C.c_double), ("min_z", C.c_double),
-                ("delta_t", C.c_double), ("delta_x", C.c_double), ("delta_z", C.c_double)]
+                ("delta_t", C.c_double), ("delta_x", C.c_double), ("delta_z", C.c_double),
+                ("d_row_support", C.c_void_p)]
 
 
 class Lattice(C.Structure):
@@ -69,6 +70,7 @@ SIGNATURES = {
     "dfcsr_make_df_workspace": (_L, [_I, _I]),
     "dfcsr_make_df": (C.c_int, [_P, _P, Axis, Axis, _I, _P, _P, _P, _D, _P, _P, _P, _P]),
     "dfcsr_history_regrid": (C.c_int, [_P, Axis, Axis, Axis, Axis, _D, _P, _I, _P, _P]),
+    "dfcsr_history_row_support": (C.c_int, [_P, _I, _I, _I, _P, _P]),
     "dfcsr_history_pack": (C.c_int, [_P, _I, _I, _I, _P, _P]),
     "dfcsr_history_unpack": (C.c_int, [_P, _I, _I, _I, _P, _P]),
     "dfcsr_wake_mesh": (C.c_int, [C.POINTER(History), C.POINTER(Lattice), C.POINTER(WakeParams),

@@ -15,6 +15,7 @@
 // identical source fields, the slice is bit-identical to scipy's.
 //
 // Bound: HBM write of X*Z*48 B per slice (the source, <= 300x300x5 doubles, stays in L2).
+#include <limits.h>
 #include "common.cuh"
 
 namespace dfcsr {
@@ -164,6 +165,49 @@ extern "C" int dfcsr_history_regrid(const double* d_fields, dfcsr_axis src_x, df
         regrid_kernel<true><<<grid, kRegridCols, 0, as_stream(stream)>>>(d_fields, sx, sz, dx, dz, fill_vx_x, d_fill_vx_x, d_slice);
     else
         regrid_kernel<false><<<grid, kRegridCols, 0, as_stream(stream)>>>(d_fields, sx, sz, dx, dz, fill_vx_x, d_fill_vx_x, d_slice);
+    count_launch(1);
+    DFCSR_CUDA_OK(cudaGetLastError());
+    return DFCSR_OK;
+}
+
+// Row support of a voxel slice: per transverse row the hull [z_lo, z_hi] of voxels with a non-zero density or density
+// gradient (dfcsr_history.d_row_support).  One warp per row, lanes stride along z.
+template <bool kF32>
+__global__ void __launch_bounds__(256)
+row_support_kernel(const void* __restrict__ slice, int X, int Z, int* __restrict__ support) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
+    for (int row = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5); row < X; row += warps) {
+        int lo = INT_MAX, hi = -1;
+        for (int z = lane; z < Z; z += 32) {
+            bool nz;
+            if (kF32) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(slice) + ((size_t)row * Z + z) * (DFCSR_VOXEL_FLOATS / 4));
+                nz = !(v.x == 0.f) || !(v.y == 0.f) || !(v.z == 0.f);
+            } else {
+                const double2* p = reinterpret_cast<const double2*>(slice) + ((size_t)row * Z + z) * (DFCSR_VOXEL_DOUBLES / 2);
+                const double2 a = __ldg(p);
+                const double b = __ldg(reinterpret_cast<const double*>(p + 1));
+                nz = !(a.x == 0.0) || !(a.y == 0.0) || !(b == 0.0);      // NaN counts as non-zero
+            }
+            if (nz) { lo = min(lo, z); hi = max(hi, z); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (lane == 0) { support[2 * row] = lo; support[2 * row + 1] = hi; }
+    }
+}
+
+extern "C" int dfcsr_history_row_support(const void* d_slice, int32_t X, int32_t Z, int32_t format, int32_t* d_support,
+                                         void* stream) {
+    DFCSR_REQUIRE(d_slice && d_support && X > 0 && Z > 0, "bad argument");
+    DFCSR_REQUIRE(format == DFCSR_VOXEL_F64 || format == DFCSR_VOXEL_F32, "unknown voxel format");
+    const long long threads = (long long)X * 32;
+    if (format == DFCSR_VOXEL_F32) row_support_kernel<true><<<blocks_for(threads, 256), 256, 0, as_stream(stream)>>>(d_slice, X, Z, d_support);
+    else row_support_kernel<false><<<blocks_for(threads, 256), 256, 0, as_stream(stream)>>>(d_slice, X, Z, d_support);
     count_launch(1);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;

@@ -70,6 +70,7 @@ class DF_tracker:
         self._x_axis_interp = None
         self._z_axis_interp = None
         self._ring = None              # (cap, X, Z, 6) device tensor
+        self._support = None           # (cap, X, 2) int32 row hulls of the non-zero density voxels, slot-aligned with the ring
         self._head = 0
         self.history: ops.DeviceHistory | None = None
         self.rebuilds = 0
@@ -172,8 +173,11 @@ class DF_tracker:
         self.time_interp.pop()
 
     # ------------------------------------------------------------------------------- ring
+    def _slot_index(self, k):
+        return (self._head + k) % self._ring.shape[0]
+
     def _slot(self, k):
-        return self._ring[(self._head + k) % self._ring.shape[0]]
+        return self._ring[self._slot_index(k)]
 
     def _ensure_ring(self, X, Z, need):
         ring = self._ring
@@ -181,6 +185,7 @@ class DF_tracker:
             cap = max(16, 1 << (max(need, 1) * 2 - 1).bit_length())
             self._ring = None          # release the old ring before allocating the new one
             self._ring = ops.new_slices((cap, X, Z), self.precision, self.device)
+            self._support = ops.new_row_support(cap, X, self.device)
             self._head = 0
             return True
         return False
@@ -192,11 +197,15 @@ class DF_tracker:
         new = torch.empty((cap,) + tuple(old.shape[1:]), dtype=old.dtype, device=self.device)
         idx = (torch.arange(T, device=self.device) + self._head) % old.shape[0]
         new[:T] = old[idx]
-        self._ring, self._head = new, 0
+        sup = ops.new_row_support(cap, old.shape[1], self.device)
+        sup[:T] = self._support[idx]
+        self._ring, self._support, self._head = new, sup, 0
 
-    def _regrid(self, rec: _Record, slot):
+    def _regrid(self, rec: _Record, idx):
+        """Re-grid one logged record into ring slot `idx` and refresh that slot's row support."""
         ops.history_regrid(rec.fields, rec.x_axis, rec.z_axis, self._x_axis_interp, self._z_axis_interp,
-                           rec.scalars[4:5], slot)
+                           rec.scalars[4:5], self._ring[idx])
+        ops.history_row_support(self._ring[idx], self._support[idx])
 
     def append_interpolant(self, formation_length, n_formation_length):
         start_point = max(0, self.end_time - n_formation_length * formation_length)    # deposit.py:313
@@ -214,7 +223,7 @@ class DF_tracker:
             self.time_interp.append(rec.t)
             if len(self.time_interp) > self._ring.shape[0]:
                 self._grow_ring()
-            self._regrid(rec, self._slot(len(self.time_interp) - 1))
+            self._regrid(rec, self._slot_index(len(self.time_interp) - 1))
             return False
         # rebuild (deposit.py:339-390)
         print("start reinterpolation. number of slice", str(len(self.time_log)))
@@ -235,7 +244,7 @@ class DF_tracker:
         self._ensure_ring(xbins, zbins, len(self.DF_log))
         self._head = 0
         for k, r in enumerate(self.DF_log):
-            self._regrid(r, self._ring[k])
+            self._regrid(r, k)
         self.rebuilds += 1
         return True
 
@@ -254,7 +263,7 @@ class DF_tracker:
         self.delta_z = (self.max_z - self.min_z) / (self.z_grid_interp.shape[0] - 1)
         self.history = ops.DeviceHistory(self._ring, self._head, T, float(self.min_x), float(self.min_y),
                                          float(self.min_z), float(self.delta_x), float(self.delta_y),
-                                         float(self.delta_z))
+                                         float(self.delta_z), self._support)
 
     # lazily materialised host copies of the (T, X, Z) stacks, reference attribute names
     def _stack(self, k):

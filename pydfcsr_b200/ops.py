@@ -240,6 +240,24 @@ def history_pack(fields, slice_out=None, precision="fp64"):
     return slice_out
 
 
+def new_row_support(cap, X, device) -> torch.Tensor:
+    """(cap, X, 2) int32 row hulls of the non-zero density voxels (dfcsr_history.d_row_support), all rows empty."""
+    sup = torch.empty((cap, X, 2), dtype=torch.int32, device=device)
+    sup[..., 0] = torch.iinfo(torch.int32).max
+    sup[..., 1] = -1
+    return sup
+
+
+def history_row_support(slice_in, support_out):
+    """Hull [z_lo, z_hi] of the voxels with non-zero density / density gradient for every row of one slice."""
+    X, Z = slice_in.shape[0], slice_in.shape[1]
+    if support_out.dtype != torch.int32 or tuple(support_out.shape) != (X, 2) or not support_out.is_contiguous():
+        raise _lib.DfcsrError("row support must be a contiguous (X, 2) int32 tensor")
+    check(lib.dfcsr_history_row_support(_ptr(slice_in), X, Z, voxel_format(slice_in), _ptr(support_out), _stream()),
+          "dfcsr_history_row_support")
+    return support_out
+
+
 def history_unpack(slice_in, X, Z):
     out = torch.empty((5, X, Z), dtype=F64, device=slice_in.device)
     check(lib.dfcsr_history_unpack(_ptr(slice_in), X, Z, voxel_format(slice_in), _ptr(out), _stream()), "dfcsr_history_unpack")
@@ -285,24 +303,32 @@ class DeviceHistory:
     delta_t: float
     delta_x: float
     delta_z: float
+    support: torch.Tensor | None = None   # (cap, X, 2) int32 row hulls of the non-zero density voxels, or None
 
     def view(self) -> _lib.History:
         cap, X, Z, elems = self.ring.shape
+        if self.support is not None and (self.support.dtype != torch.int32 or tuple(self.support.shape) != (cap, X, 2)
+                                         or not self.support.is_contiguous()):
+            raise _lib.DfcsrError("row support must be a contiguous (cap, X, 2) int32 tensor")
         return _lib.History(self.ring.data_ptr(), X * Z * elems, cap, self.head, self.T, X, Z, voxel_format(self.ring),
-                            self.min_t, self.min_x, self.min_z, self.delta_t, self.delta_x, self.delta_z)
+                            self.min_t, self.min_x, self.min_z, self.delta_t, self.delta_x, self.delta_z,
+                            None if self.support is None else self.support.data_ptr())
 
     @classmethod
     def from_stacks(cls, stacks, min_t, min_x, min_z, delta_t, delta_x, delta_z, device, cap=None, head=0,
-                    precision="fp64"):
+                    precision="fp64", row_support=True):
         """Import five host (T, X, Z) arrays in dfcsr_field order (oracle / golden histories)."""
         T, X, Z = stacks[0].shape
         cap = cap or T
         ring = new_slices((cap, X, Z), precision, device).zero_()
+        support = new_row_support(cap, X, device) if row_support else None
         for k in range(T):
             fields = torch.from_numpy(np.ascontiguousarray(np.stack([s[k] for s in stacks]))).to(device)
             history_pack(fields, ring[(head + k) % cap])
+            if support is not None:
+                history_row_support(ring[(head + k) % cap], support[(head + k) % cap])
         return cls(ring, head, T, float(min_t), float(min_x), float(min_z), float(delta_t), float(delta_x),
-                   float(delta_z))
+                   float(delta_z), support)
 
 
 def wake_params(t, sigma_x, sigma_z, slope0, mean_x, formation_window, csr_scaling, nx, nz) -> _lib.WakeParams:

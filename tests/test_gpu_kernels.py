@@ -178,15 +178,15 @@ def test_wake_mesh_matches_oracle(dev, tilt):
     s = sc["scalars"]
     xm, zm, _, _ = O.observation_mesh(x, z, s["slope"], s["sigma_z"], s["mean_z"], 3, 3, 5, 7)
     import torch
-    cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(3, dtype=torch.int64, device=dev)
     de, kick = ops.wake_mesh(hist, dlat, wp, _up(xm, dev), _up(zm, dev), counters=cnt)
     ref_de, ref_kick = O.wake_mesh(xm, zm, osc, sc["lattice"], sc["stack"])
     assert _rel(de.cpu().numpy(), ref_de) < TOL
     assert _rel(kick.cpu().numpy(), ref_kick) < TOL
     big = np.abs(ref_de) > 1e-3 * np.max(np.abs(ref_de))
     assert np.max(np.abs(de.cpu().numpy()[big] / ref_de[big] - 1)) < 1e-9
-    n_in, n_all = (int(v) for v in cnt.cpu())
-    assert n_all == xm.size * (4 if abs(tilt) <= 1 else 5) * nx * nz and 0 < n_in < n_all
+    n_in, n_all, n_gat = (int(v) for v in cnt.cpu())
+    assert n_all == xm.size * (4 if abs(tilt) <= 1 else 5) * nx * nz and 0 < n_gat <= n_in < n_all
     # block split (CSR.py:121-125): any contiguous block gives the same numbers
     de2, _ = ops.wake_mesh(hist, dlat, wp, _up(xm, dev), _up(zm, dev), first=11, count=9)
     assert np.array_equal(de2.cpu().numpy(), de.cpu().numpy()[11:20])
@@ -340,7 +340,7 @@ def test_track_linear_kernel_matches_host_maps(dev):
 # K4 kernel variants (developer knob DFCSR_WAKE_CFG, read per launch): every shipped variant must meet the same
 # gate as the default.  1 = round-1 s'-lane kernel, 10 = x'-lane register-cached kernel, 20 = trimmed s'-lane
 # kernel, 21/25 = two x' nodes per lane (CTA shapes 2x256 / 2x192 threads per SM).
-@pytest.mark.parametrize("cfg", [0, 1, 10, 20, 25, 30, 40])
+@pytest.mark.parametrize("cfg", [0, 1, 10, 20, 25, 30, 40, 45, 46])
 @pytest.mark.parametrize("tilt", [0.0, 2.5])
 def test_wake_kernel_variants_match_oracle(dev, monkeypatch, cfg, tilt):
     from pydfcsr_b200 import ops
@@ -352,16 +352,17 @@ def test_wake_kernel_variants_match_oracle(dev, monkeypatch, cfg, tilt):
     s = sc["scalars"]
     xm, zm, _, _ = O.observation_mesh(x, z, s["slope"], s["sigma_z"], s["mean_z"], 3, 3, 5, 7)
     import torch
-    cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(3, dtype=torch.int64, device=dev)
     de, kick = ops.wake_mesh(hist, dlat, wp, _up(xm, dev), _up(zm, dev), counters=cnt)
     ref_de, ref_kick = O.wake_mesh(xm, zm, osc, sc["lattice"], sc["stack"])
     assert _rel(de.cpu().numpy(), ref_de) < TOL
     assert _rel(kick.cpu().numpy(), ref_kick) < TOL
-    n_in, n_all = (int(v) for v in cnt.cpu())
-    assert n_all == xm.size * (4 if abs(tilt) <= 1 else 5) * nx * nz and 0 < n_in < n_all
+    n_in, n_all, n_gat = (int(v) for v in cnt.cpu())
+    assert n_all == xm.size * (4 if abs(tilt) <= 1 else 5) * nx * nz and 0 < n_gat <= n_in < n_all
+    assert n_gat == n_in or cfg in (0, 46)    # only the default kernel skips zero-density samples (46 = forced on)
     # the in-grid sample count is a property of the quadrature, not of the kernel variant
     monkeypatch.setenv("DFCSR_WAKE_CFG", "1")
-    cnt1 = torch.zeros(2, dtype=torch.int64, device=dev)
+    cnt1 = torch.zeros(3, dtype=torch.int64, device=dev)
     ops.wake_mesh(hist, dlat, wp, _up(xm, dev), _up(zm, dev), counters=cnt1)
     assert int(cnt1[0]) == n_in
     # run-to-run bitwise reproducible
@@ -377,3 +378,73 @@ def test_fused_sqrt_is_bitwise_the_library_sqrt(dev):
     for seed, (lo, hi) in enumerate([(-60.0, 8.0), (-2.0, 2.0), (-1000.0, 1000.0)]):
         bad_r, bad_y = ops.selftest_sqrt(200_000_000, seed=seed + 1, lo_exp=lo, hi_exp=hi)
         assert bad_r == 0 and bad_y == 0, (lo, hi, bad_r, bad_y)
+
+
+@pytest.mark.parametrize("tilt", [0.0, 2.5, -2.5])
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_zero_density_skipping_is_exact(dev, monkeypatch, tilt, precision):
+    """dfcsr_history.d_row_support: samples whose eight voxels carry no density and no density gradient add exactly
+    0 (every integrand term has a factor rho' or grad rho', CSR.py:732-775), so K4 skips them without loading the
+    history.  The result must be BITWISE the one computed without the support table, and on a tilted beam most of
+    the in-grid samples must actually be skipped."""
+    import torch
+    from pydfcsr_b200 import ops
+    monkeypatch.setenv("DFCSR_WAKE_CFG", "46")      # skipping on for every slope (the default enables it for |slope| > 1)
+    sc = scenario.chicane_entry(tilt=tilt)
+    st, lat = sc["stack"], sc["lattice"]
+    nx = nz = 50
+    args = ([st.data[k] for k in O.FIELDS], st.min_x, st.min_y, st.min_z, st.delta_x, st.delta_y, st.delta_z, dev)
+    h_on = ops.DeviceHistory.from_stacks(*args, cap=st.shape[0] + 3, head=2, precision=precision)
+    h_off = ops.DeviceHistory.from_stacks(*args, cap=st.shape[0] + 3, head=2, precision=precision, row_support=False)
+    assert h_on.support is not None and h_off.support is None
+    dlat = ops.DeviceLattice.upload(lat.coords, lat.n_vec, lat.tau_vec, lat.rho, lat.distance, lat.min_s, lat.delta_s, dev)
+    wp = ops.wake_params(nx=nx, nz=nz, **sc["wake_scalars"])
+    x, z = sc["coords"][0], sc["coords"][4]
+    s = sc["scalars"]
+    xm, zm, _, _ = O.observation_mesh(x, z, s["slope"], s["sigma_z"], s["mean_z"], 3, 3, 5, 7)
+    c_on = torch.zeros(3, dtype=torch.int64, device=dev)
+    c_off = torch.zeros(3, dtype=torch.int64, device=dev)
+    de1, k1 = ops.wake_mesh(h_on, dlat, wp, _up(xm, dev), _up(zm, dev), counters=c_on)
+    de0, k0 = ops.wake_mesh(h_off, dlat, wp, _up(xm, dev), _up(zm, dev), counters=c_off)
+    assert torch.equal(de1, de0) and torch.equal(k1, k0)
+    on, off = [int(v) for v in c_on.cpu()], [int(v) for v in c_off.cpu()]
+    assert on[0] == off[0] and on[1] == off[1] and off[2] == off[0] and 0 < on[2] <= on[0]
+    if tilt != 0.0:
+        assert on[2] < 0.9 * on[0], on          # the tilted bunch fills a band of the history grid (72 % here)
+    # the support table is what the oracle's stack says: hull of the voxels with rho, rho_x or rho_z != 0
+    cap, head = h_on.ring.shape[0], 2
+    sup = h_on.support.cpu().numpy()
+    fld = [st.data[k] for k in O.FIELDS[:3]]
+    if precision == "fp32":
+        fld = [f.astype(np.float32) for f in fld]
+    nzm = (fld[0] != 0) | (fld[1] != 0) | (fld[2] != 0)
+    for k in range(st.shape[0]):
+        rows = nzm[k].any(axis=1)
+        lo = np.where(rows, nzm[k].argmax(axis=1), np.iinfo(np.int32).max)
+        hi = np.where(rows, nzm.shape[2] - 1 - nzm[k][:, ::-1].argmax(axis=1), -1)
+        assert np.array_equal(sup[(head + k) % cap, :, 0], lo) and np.array_equal(sup[(head + k) % cap, :, 1], hi)
+
+
+def test_zero_density_skipping_empty_and_full_rows(dev, monkeypatch):
+    """Degenerate supports: an all-zero history gives exactly zero wakes without gathering anything; a history
+    without a single zero voxel skips nothing."""
+    import torch
+    from pydfcsr_b200 import ops
+    monkeypatch.setenv("DFCSR_WAKE_CFG", "46")
+    sc = scenario.chicane_entry(tilt=0.0)
+    st, lat = sc["stack"], sc["lattice"]
+    dlat = ops.DeviceLattice.upload(lat.coords, lat.n_vec, lat.tau_vec, lat.rho, lat.distance, lat.min_s, lat.delta_s, dev)
+    wp = ops.wake_params(nx=20, nz=33, **sc["wake_scalars"])
+    x, z = sc["coords"][0], sc["coords"][4]
+    s = sc["scalars"]
+    xm, zm, _, _ = O.observation_mesh(x, z, s["slope"], s["sigma_z"], s["mean_z"], 3, 3, 3, 4)
+    for fill in (0.0, 1.0):
+        stacks = [np.full(st.shape, fill) for _ in O.FIELDS]
+        h = ops.DeviceHistory.from_stacks(stacks, st.min_x, st.min_y, st.min_z, st.delta_x, st.delta_y, st.delta_z, dev)
+        cnt = torch.zeros(3, dtype=torch.int64, device=dev)
+        de, kick = ops.wake_mesh(h, dlat, wp, _up(xm, dev), _up(zm, dev), counters=cnt)
+        n_in, _, n_gat = (int(v) for v in cnt.cpu())
+        if fill == 0.0:
+            assert n_gat == 0 and n_in > 0 and not de.any() and not kick.any()
+        else:
+            assert n_gat == n_in > 0 and bool(de.abs().max() > 0)

@@ -30,7 +30,7 @@ inp = {"input_beam": {"style": "synthetic", "n_particle": n_particle, "seed": 0}
                                workdir="/tmp/dfcsr_profile", xbins=mx, zbins=mz, xlim=5, zlim=5)}
 csr = CSR2D(inp, parallel=parallel, verbose=False)
 rank, world = (csr.rank, csr.world_size) if parallel else (0, 1)
-counters = torch.zeros(2, dtype=torch.int64, device=csr.device)
+counters = torch.zeros(3, dtype=torch.int64, device=csr.device)
 csr.wake_counters = counters
 log = []
 inner = csr.calculate_2D_CSR_parallel if parallel else csr.calculate_2D_CSR

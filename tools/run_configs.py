@@ -98,7 +98,7 @@ def main(names):
         ev[1].record()
         torch.cuda.synchronize()
         csr.get_CSR_mesh()
-        csr.wake_counters = torch.zeros(2, dtype=torch.int64, device=beam.x.device)
+        csr.wake_counters = torch.zeros(3, dtype=torch.int64, device=beam.x.device)
         ev[2].record()
         for _ in range(reps):
             csr.calculate_2D_CSR()
@@ -108,7 +108,7 @@ def main(names):
         n_mesh = csr.CSR_params.xbins * csr.CSR_params.zbins
         counters = [int(v) // reps for v in csr.wake_counters.cpu()]      # [in-grid samples, samples the reference evaluates]
         csr.wake_counters = None
-        in_grid = f"{counters[0] / counters[1]:.3f}" if counters[1] else "-"
+        in_grid = f"{counters[0] / counters[1]:.3f}/{counters[2] / counters[1]:.3f}" if counters[1] else "-"
         rate = f"{counters[1] / (k4_ms * 1e-3):.3e}" if counters[1] else "-"
         de, kick = csr.dE_dct.cpu().numpy().ravel(), csr.x_kick.cpu().numpy().ravel()
         rng = np.random.default_rng(0)
