@@ -195,7 +195,8 @@ int dfcsr_history_unpack(const void* d_slice, int32_t X, int32_t Z, int32_t form
 /* ---- A10-A12 / K4 wake on the observation mesh (CSR.py:397-451, 454-602, 605-782) --------------
  * For k in [0, count): s = t + d_zmesh[first + k], x = d_xmesh[first + k];
  * d_dE[k], d_kick[k] = get_CSR_wake(s, x).  first/count implement the reference's MPI block split
- * (CSR.py:121-125, 434-445).  d_counters (may be NULL, else THREE counters): [0] += in-grid integrand samples,
+ * (CSR.py:121-125, 434-445).  d_counters (may be NULL, else THREE counters): [0] += in-grid integrand samples the
+ * kernel located (with d_row_support, s' nodes that provably miss the band of non-zero density rows are not swept),
  * [1] += samples the reference evaluates, [2] += in-grid samples whose history voxels were actually gathered
  * (= [0] without d_row_support) -- device-side accounting for the roofline figure. */
 int dfcsr_wake_mesh(const dfcsr_history* hist, const dfcsr_lattice* lat, const dfcsr_wake_params* wp,

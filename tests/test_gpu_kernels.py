@@ -364,7 +364,7 @@ def test_wake_kernel_variants_match_oracle(dev, monkeypatch, cfg, tilt):
     monkeypatch.setenv("DFCSR_WAKE_CFG", "1")
     cnt1 = torch.zeros(3, dtype=torch.int64, device=dev)
     ops.wake_mesh(hist, dlat, wp, _up(xm, dev), _up(zm, dev), counters=cnt1)
-    assert int(cnt1[0]) == n_in
+    assert int(cnt1[0]) == n_in or (cfg in (0, 46) and n_in < int(cnt1[0]))   # s' nodes outside the density band are not swept
     # run-to-run bitwise reproducible
     monkeypatch.setenv("DFCSR_WAKE_CFG", str(cfg))
     de2, kick2 = ops.wake_mesh(hist, dlat, wp, _up(xm, dev), _up(zm, dev))
@@ -408,9 +408,9 @@ def test_zero_density_skipping_is_exact(dev, monkeypatch, tilt, precision):
     de0, k0 = ops.wake_mesh(h_off, dlat, wp, _up(xm, dev), _up(zm, dev), counters=c_off)
     assert torch.equal(de1, de0) and torch.equal(k1, k0)
     on, off = [int(v) for v in c_on.cpu()], [int(v) for v in c_off.cpu()]
-    assert on[0] == off[0] and on[1] == off[1] and off[2] == off[0] and 0 < on[2] <= on[0]
+    assert on[0] <= off[0] and on[1] == off[1] and off[2] == off[0] and 0 < on[2] <= on[0]
     if tilt != 0.0:
-        assert on[2] < 0.9 * on[0], on          # the tilted bunch fills a band of the history grid (72 % here)
+        assert on[2] < 0.9 * off[0], (on, off)   # the tilted bunch fills a band of the history grid (72 % here)
     # the support table is what the oracle's stack says: hull of the voxels with rho, rho_x or rho_z != 0
     cap, head = h_on.ring.shape[0], 2
     sup = h_on.support.cpu().numpy()
@@ -445,6 +445,6 @@ def test_zero_density_skipping_empty_and_full_rows(dev, monkeypatch):
         de, kick = ops.wake_mesh(h, dlat, wp, _up(xm, dev), _up(zm, dev), counters=cnt)
         n_in, _, n_gat = (int(v) for v in cnt.cpu())
         if fill == 0.0:
-            assert n_gat == 0 and n_in > 0 and not de.any() and not kick.any()
+            assert n_gat == 0 and n_in == 0 and not de.any() and not kick.any()      # every x' node is dropped up front
         else:
             assert n_gat == n_in > 0 and bool(de.abs().max() > 0)

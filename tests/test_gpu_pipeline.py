@@ -158,6 +158,39 @@ def test_run_is_bit_reproducible():
         assert torch.equal(u, v)
 
 
+def test_zero_density_skipping_is_bitwise_through_the_whole_chicane(monkeypatch):
+    """All 133 steps of the chicane (both quadrature branches, |slope| up to ~100, rebuilds, reversed rectangles early
+    on) with the wake applied at every evaluation: the run with zero-density skipping (row hulls + coarse s' bracket,
+    DESIGN.md section 4 (vi)) and the run without it (DFCSR_WAKE_CFG=45) must end with the SAME BITS in the last wake
+    grids and in every particle coordinate -- any sample dropped by mistake would have kicked the beam differently."""
+    import torch
+    from pydfcsr_b200 import CSR2D, synth
+
+    def run(cfg):
+        if cfg is None:
+            monkeypatch.delenv("DFCSR_WAKE_CFG", raising=False)
+        else:
+            monkeypatch.setenv("DFCSR_WAKE_CFG", cfg)
+        inp = {"input_beam": {"style": "synthetic", "n_particle": 200_000, "seed": 7},
+               "input_lattice": {"lattice_config": synth.chicane_lattice_config()},
+               "particle_deposition": dict(xbins=120, zbins=120, xlim=5, zlim=5, filter_order=1, filter_window=9,
+                                           velocity_threhold=1000, upper_limit=1000),
+               "CSR_integration": dict(n_formation_length=1, zbins=70, xbins=60),
+               "CSR_computation": dict(compute_CSR=1, apply_CSR=1, transverse_on=1, xbins=6, zbins=9, xlim=3, zlim=3,
+                                       write_beam=None, write_wakes=False, workdir="/tmp/dfcsr_test")}
+        csr = CSR2D(inp, parallel=False, device="cuda:0", verbose=False)
+        csr.wake_counters = torch.zeros(3, dtype=torch.int64, device="cuda:0")
+        csr.run()
+        return csr.dE_dct.clone(), csr.x_kick.clone(), torch.stack(csr.beam.coords), [int(v) for v in csr.wake_counters.cpu()]
+
+    on, off = run(None), run("45")
+    assert float(on[0].abs().max()) > 0
+    for u, v in zip(on[:3], off[:3]):
+        assert torch.equal(u, v)
+    # over the run, most in-grid samples were never gathered (the chirped bunch is a thin band of its grid)
+    assert off[3][2] == off[3][0] and on[3][2] < 0.7 * off[3][0], (on[3], off[3])
+
+
 def test_csr2d_full_chicane_shadowed_by_oracle():
     """The whole 133-step chicane through CSR2D.run() on the device, shadowed step by step by the CPU
     oracle fed with the device's particle batches: same grid-branch / window / rebuild decisions, and
