@@ -41,6 +41,7 @@ extern "C" {
 #define DFCSR_STATS_DOUBLES 16
 #define DFCSR_DF_SCALARS 8
 #define DFCSR_MAX_ELEMENTS 256
+#define DFCSR_MAX_PEERS 8          /* ranks of one NVLink/NVSwitch box (dfcsr_wake_grid_peers) */
 
 typedef enum dfcsr_status {
     DFCSR_OK = 0,
@@ -211,6 +212,18 @@ int dfcsr_wake_grid(const dfcsr_history* hist, const dfcsr_lattice* lat, const d
                     dfcsr_axis x_axis, dfcsr_axis z_axis, double slope, double intercept,
                     int64_t first, int64_t count, double* d_dE, double* d_kick,
                     unsigned long long* d_counters, void* stream);
+
+/* K4 fused with the exchange step (comm.Allgatherv x2, CSR.py:447-448).  Instead of filling a local send buffer that a
+ * collective then distributes, the kernel stores both results of every observation point of this rank's block
+ * straight into the wake grid of EVERY rank through NVLink peer mappings: h_peer_grids holds n_peers HOST entries,
+ * entry p = the address, valid in THIS process (CUDA IPC / symmetric-memory mapping; this rank's own entry is its
+ * local buffer), of rank p's (2, x_axis.n * z_axis.n) fp64 grid [dE | kick]; point k of the block lands at index
+ * first + k of both halves.  The caller orders the launch after the peers' last readers of those grids and publishes
+ * completion with a barrier across ranks (pydfcsr_b200/distributed.py: two alternating grids + one barrier per step). */
+int dfcsr_wake_grid_peers(const dfcsr_history* hist, const dfcsr_lattice* lat, const dfcsr_wake_params* wp,
+                          dfcsr_axis x_axis, dfcsr_axis z_axis, double slope, double intercept,
+                          int64_t first, int64_t count, const uint64_t* h_peer_grids, int32_t n_peers,
+                          unsigned long long* d_counters, void* stream);
 
 /* get_CSR_wake(s, x, debug=True) (CSR.py:571-572, 599-600): integrands of one point.
  * d_iz / d_ix receive the regions back to back, each (n_x, n_s) row-major like the reference's

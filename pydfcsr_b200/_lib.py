@@ -18,6 +18,7 @@ LATTICE_DOUBLES = 6
 STATS_DOUBLES = 16
 DF_SCALARS = 8
 ABI_VERSION = 2
+MAX_PEERS = 8
 
 # indices of dfcsr_stat
 (S_MEAN_X, S_MEAN_Z, S_SIGMA_X, S_SIGMA_Z, S_SLOPE, S_INTERCEPT, S_MEAN_XT, S_SIGMA_XT,
@@ -77,6 +78,8 @@ SIGNATURES = {
                                   _P, _P, _L, _L, _P, _P, _P, _P]),
     "dfcsr_wake_grid": (C.c_int, [C.POINTER(History), C.POINTER(Lattice), C.POINTER(WakeParams), Axis, Axis, _D, _D,
                                   _L, _L, _P, _P, _P, _P]),
+    "dfcsr_wake_grid_peers": (C.c_int, [C.POINTER(History), C.POINTER(Lattice), C.POINTER(WakeParams), Axis, Axis, _D, _D,
+                                        _L, _L, C.POINTER(C.c_uint64), _I, _P, _P]),
     "dfcsr_wake_point_debug": (C.c_int, [C.POINTER(History), C.POINTER(Lattice), C.POINTER(WakeParams),
                                          _D, _D, _P, _P, _L, _P, _P, _P]),
     "dfcsr_apply_kick": (C.c_int, [_P, _P, _P, _P, _L, _D, _D, _P, _P, Axis, Axis, _D, _D, _I, _P]),

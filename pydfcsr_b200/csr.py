@@ -130,6 +130,8 @@ class CSR2D:
         n = self.CSR_params.xbins * self.CSR_params.zbins
         self.count, displ = dist_utils.split_counts(n, self.world_size)
         self.displ = np.array(displ)
+        # fused K4 + exchange over NVLink peer memory when the ranks can map each other's grids, else NCCL
+        self._peer_grid = dist_utils.make_peer_wake_grid(n, self.device)
 
     # ------------------------------------------------------------------------------- run loop
     def get_formation_length(self, R, sigma_z, phi=0.0, inbend=True):
@@ -297,17 +299,28 @@ class CSR2D:
         self.x_kick = kick.reshape(p.xbins, p.zbins)
 
     def calculate_2D_CSR_parallel(self):
-        """CSR.py:420-451: this rank's contiguous block, then one all-gather of [dE | kick]."""
+        """CSR.py:420-451: this rank's contiguous block.  With peer memory the wake kernel stores its results into
+        the grids of all ranks itself (fused exchange) and one barrier publishes them; otherwise one NCCL all-gather
+        of [dE | kick] replaces the two Allgatherv calls."""
         p = self.CSR_params
         n = p.xbins * p.zbins
         lat = self.lattice.device_tables(self.device)
-        pad = max(self.count)
-        send = torch.zeros((2, pad), dtype=torch.float64, device=self.device)
         xa, za = self._mesh_axes
-        ops.wake_grid(self.DF_tracker.history, lat, self._wake_params(), xa, za, *self._mesh_slope,
-                      first=int(self.displ[self.rank]), count=int(self.count[self.rank]), out=send,
-                      counters=getattr(self, "wake_counters", None))
-        full = dist_utils.all_gather_blocks(send, self.count, n)
+        peer = getattr(self, "_peer_grid", None)
+        if peer is not None:
+            grid, ptrs, handle = peer.next()
+            ops.wake_grid_peers(self.DF_tracker.history, lat, self._wake_params(), xa, za, *self._mesh_slope,
+                                first=int(self.displ[self.rank]), count=int(self.count[self.rank]), peer_ptrs=ptrs,
+                                counters=getattr(self, "wake_counters", None))
+            handle.barrier(channel=0)
+            full = grid.clone()          # value semantics like the NCCL path: the mapped grid is rewritten two steps later
+        else:
+            pad = max(self.count)
+            send = torch.zeros((2, pad), dtype=torch.float64, device=self.device)
+            ops.wake_grid(self.DF_tracker.history, lat, self._wake_params(), xa, za, *self._mesh_slope,
+                          first=int(self.displ[self.rank]), count=int(self.count[self.rank]), out=send,
+                          counters=getattr(self, "wake_counters", None))
+            full = dist_utils.all_gather_blocks(send, self.count, n)
         self.dE_dct = full[0].reshape(p.xbins, p.zbins)
         self.x_kick = full[1].reshape(p.xbins, p.zbins)
 

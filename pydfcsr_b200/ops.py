@@ -363,6 +363,16 @@ def wake_grid(hist: DeviceHistory, lat: DeviceLattice, wp: _lib.WakeParams, x_ax
     return out[0][:count], out[1][:count]
 
 
+def wake_grid_peers(hist: DeviceHistory, lat: DeviceLattice, wp: _lib.WakeParams, x_axis: Axis, z_axis: Axis, slope,
+                    intercept, first, count, peer_ptrs, counters=None):
+    """K4 fused with the exchange (dfcsr_wake_grid_peers): block [first, first+count) of the mesh is computed here and
+    stored into every rank's (2, N) grid; `peer_ptrs` = ctypes array of the grids' addresses as mapped in this process."""
+    hv, lv = hist.view(), lat.view()
+    check(lib.dfcsr_wake_grid_peers(C.byref(hv), C.byref(lv), C.byref(wp), x_axis, z_axis, float(slope), float(intercept),
+                                    int(first), int(count), peer_ptrs, len(peer_ptrs), _ptr(counters), _stream()),
+          "dfcsr_wake_grid_peers")
+
+
 def wake_point_debug(hist: DeviceHistory, lat: DeviceLattice, wp: _lib.WakeParams, s: float, x: float):
     """Integrand arrays of one point, region by region (get_CSR_wake(debug=True), CSR.py:571-600)."""
     cap = 5 * wp.nx * wp.nz

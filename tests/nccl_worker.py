@@ -26,8 +26,19 @@ csr.calculate_2D_CSR()                      # serial launch on this rank, same s
 for a, b in ((par[0], csr.dE_dct), (par[1], csr.x_kick)):
     err = float((a - b).abs().max() / b.abs().max())
     assert err < 1e-12, f"sharded != serial: {err:.3e}"
+# fused K4 + exchange over peer memory (default when the ranks can map each other's grids) against the NCCL all-gather:
+# the same kernel computes the same block either way, so the two grids must agree to the last bit
+path = "fused" if csr._peer_grid is not None else "nccl"
+if csr._peer_grid is not None:
+    for _ in range(3):                       # both alternating grids, several rounds
+        csr.calculate_2D_CSR_parallel()
+        assert torch.equal(csr.dE_dct, par[0]) and torch.equal(csr.x_kick, par[1]), "fused exchange not reproducible"
+    keep, csr._peer_grid = csr._peer_grid, None
+    csr.calculate_2D_CSR_parallel()
+    assert torch.equal(csr.dE_dct, par[0]) and torch.equal(csr.x_kick, par[1]), "fused exchange != NCCL all-gather"
+    csr._peer_grid = keep
 gathered = [torch.empty_like(par[0]) for _ in range(csr.world_size)]
 torch.distributed.all_gather(gathered, par[0])
 assert all(torch.equal(g, par[0]) for g in gathered), "ranks disagree"
-os.write(1, f"nccl ok {csr.rank}\n".encode())        # one write per rank: print() pieces interleave across ranks
+os.write(1, f"nccl ok {csr.rank} exchange={path}\n".encode())        # one write per rank: print() pieces interleave across ranks
 torch.distributed.destroy_process_group()

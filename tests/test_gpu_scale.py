@@ -173,3 +173,4 @@ def test_two_rank_nccl_pipeline():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "nccl ok 0" in out.stdout and "nccl ok 1" in out.stdout
+    print(out.stdout[-300:])          # which exchange ran (fused peer-memory stores or the NCCL fallback)
