@@ -424,7 +424,10 @@ def gpu_arm(args):
                    "samples_per_point": spp, "position_m": wl["position"],
                    "l2": "256 MiB device memset between steps (inside the timed region)",
                    "points_per_gpu": n_pts // world,
-                   "parallelism": f"obs-mesh block split x{world} (4096 points per GPU), NCCL all-gather" if parallel else "single GPU"},
+                   "parallelism": (f"obs-mesh block split x{world} (4096 points per GPU), " +
+                                   ("exchange fused into K4 (NVLink peer-memory stores + one barrier)"
+                                    if getattr(csr, "_peer_grid", None) is not None else "NCCL all-gather"))
+                   if parallel else "single GPU"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "ms_per_step_unpipelined": ms_e2e_serial / args.steps,
                 "how": "per step: x, px, z, pz H2D from pinned host memory, hot path, px, pz and both wake grids D2H; "
