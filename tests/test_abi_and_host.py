@@ -116,6 +116,8 @@ for n in (7, 10, 4096):
     send[:, :count[rank]] = torch.from_numpy(full[:, displ[rank]:displ[rank] + count[rank]])
     got = D.all_gather_blocks(send, count, n).numpy()
     assert np.array_equal(got, full), (rank, n)
+# the fused K4 exchange needs NCCL ranks with CUDA peer mappings: on gloo/CPU the collective decision is "NCCL path"
+assert D.make_peer_wake_grid(4096, torch.device("cpu")) is None
 dist.barrier()
 open(os.path.join(sys.argv[2], f"ok{rank}"), "w").write("ok")     # one file per rank: stdout of two ranks interleaves
 '''

@@ -178,3 +178,67 @@ def test_twiss_matches_reference(ref):
     assert set(got) == set(want)
     for k in want:
         assert abs(got[k] - want[k]) <= 1e-12 * abs(want[k]), k
+
+
+@pytest.mark.parametrize("tilt", [0.0, 2.5])
+def test_samples_without_density_contribute_exactly_zero_in_the_reference(ref, tilt, tmp_path):
+    """The property K4's zero-density skipping rests on, checked on the UNMODIFIED reference:
+    wherever the eight history voxels of a sample hold density = d(density)/dx = d(density)/dz = 0, the reference's own
+    get_CSR_integrand (CSR.py:605-782) returns exactly 0 for both integrands -- every term carries rho' or grad rho'."""
+    import yaml
+    from pydfcsr_b200 import synth
+    lat_yaml = str(tmp_path / "lat.yaml")
+    with open(lat_yaml, "w") as fh:
+        yaml.safe_dump(dict(synth.chicane_lattice_config()), fh, sort_keys=False)
+    sc = scenario.chicane_entry(tilt=tilt)
+    csr = refstub.make_reference_csr(lat_yaml, scenario.DEPOSIT_CFG, dict(n_formation_length=1, zbins=40, xbins=40),
+                                     dict(xbins=3, zbins=4, xlim=3, zlim=3, workdir=str(tmp_path)))
+    for st in sc["steps"]:
+        x, px, y, py, z, pz = st["coords"]
+        csr.DF_tracker.get_DF(x=x, z=z, px=px, t=st["pos"])
+        csr.DF_tracker.append_DF()
+        csr.DF_tracker.append_interpolant(formation_length=st["formation_length"], n_formation_length=1)
+    csr.DF_tracker.build_interpolant()
+    x, px, y, py, z, pz = sc["coords"]
+    csr.beam = refstub.FakeBeam(x, px, z, pz, sc["pos"])
+    csr.CSR_scaling = 8.98755e3 * 1e-9
+    csr.formation_length = sc["steps"][-1]["formation_length"]
+    hs, lat = sc["stack"], sc["lattice"]
+    T, X, Z = hs.shape
+    nzv = (hs.data["density"] != 0) | (hs.data["density_x"] != 0) | (hs.data["density_z"] != 0)
+    osc = O.WakeScalars(nx=40, nz=40, **sc["wake_scalars"])
+    s_obs = sc["pos"] + 0.4 * sc["wake_scalars"]["sigma_z"]
+    x_obs = 0.3 * sc["wake_scalars"]["sigma_x"] + sc["wake_scalars"]["slope0"] * 0.4 * sc["wake_scalars"]["sigma_z"]
+    n_zero = n_in = 0
+    for (xa, xb, n_x, sa, sb, n_s) in O.wake_regions(s_obs, x_obs, osc):
+        xm, sm = np.meshgrid(np.linspace(xa, xb, n_x), np.linspace(sa, sb, n_s), indexing="ij")
+        with np.errstate(all="ignore"):
+            iz, ix = csr.get_CSR_integrand(s=s_obs, t=sc["pos"], x=x_obs, xp=xm, sp=sm)
+        # locate every sample with the reference's cell rule (interp3D.py:30-52) on the same geometry
+        def orbit(q, tab):
+            return O.interp1d(q, tab, lat.min_s, lat.delta_s)
+        q = sm.ravel()
+        rx = orbit(np.array([s_obs]), lat.coords[:, 0])[0] - orbit(q, lat.coords[:, 0]) \
+            + x_obs * orbit(np.array([s_obs]), lat.n_vec[:, 0])[0] - xm.ravel() * orbit(q, lat.n_vec[:, 0])
+        ry = orbit(np.array([s_obs]), lat.coords[:, 1])[0] - orbit(q, lat.coords[:, 1]) \
+            + x_obs * orbit(np.array([s_obs]), lat.n_vec[:, 1])[0] - xm.ravel() * orbit(q, lat.n_vec[:, 1])
+        t_ret = sc["pos"] - np.sqrt(rx ** 2 + ry ** 2)
+        ut = (t_ret - hs.min_x) / hs.delta_x
+        uy = (xm.ravel() - hs.min_y) / hs.delta_y
+        uz = (q - t_ret - hs.min_z) / hs.delta_z
+        inside = (ut > -1) & (ut < T) & (uy > -1) & (uy < X) & (uz > -1) & (uz < Z)
+        t0, y0, z0 = (np.where(inside, u, 0).astype(np.int64) for u in (ut, uy, uz))
+        t1, y1, z1 = np.minimum(t0 + 1, T - 1), np.minimum(y0 + 1, X - 1), np.minimum(z0 + 1, Z - 1)
+        any_density = np.zeros(q.shape, bool)
+        for a in (t0, t1):
+            for b in (y0, y1):
+                for c in (z0, z1):
+                    any_density |= nzv[a, b, c]
+        empty = inside & ~any_density
+        n_zero += int(empty.sum())
+        n_in += int(inside.sum())
+        assert np.all(iz.ravel()[empty] == 0.0) and np.all(ix.ravel()[empty] == 0.0)
+        assert np.all(iz.ravel()[~inside] == 0.0) and np.all(ix.ravel()[~inside] == 0.0)
+    assert n_in > 0 and n_zero > 0
+    if tilt:
+        assert n_zero > 0.2 * n_in, (n_zero, n_in)         # a chirped bunch leaves most of its +-5 sigma grid empty

@@ -15,7 +15,7 @@ import bench  # noqa: E402
 from pydfcsr_b200 import CSR2D  # noqa: E402
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-cfgs = [int(a) for a in sys.argv[2:]] or [1, 10, 20, 25, 30, 40, 0]
+cfgs = [int(a) for a in sys.argv[2:]] or [1, 10, 20, 25, 30, 40, 45, 46, 0]
 wl = bench.WORKLOAD
 inp = bench._input_dict(wl)
 tilt = os.environ.get("DFCSR_TILT")
