@@ -84,14 +84,21 @@ class Beam:
 
     # ------------------------------------------------------------------------------- state
     def update_status(self):
-        """One pass of the device reductions replaces np.std/np.mean/np.polyfit (beams.py:88-98)."""
-        st = ops.beam_stats(self.x, self.z, self.pz)
-        self.stats = st
-        self._sigma_x = float(st[_lib.S_SIGMA_X])
-        self._sigma_z = float(st[_lib.S_SIGMA_Z])
-        self._slope = np.array([st[_lib.S_SLOPE], st[_lib.S_INTERCEPT]])
-        self._mean_x = float(st[_lib.S_MEAN_X])
-        self._mean_z = float(st[_lib.S_MEAN_Z])
+        """One pass of the device reductions replaces np.std/np.mean/np.polyfit (beams.py:88-98).  The pass is only
+        ENQUEUED here; the host waits for it when a statistic is first read (`stats`, `_sigma_x`, `_slope`, ...), so the
+        caller can keep launching work -- the reduction that follows a kick overlaps with whatever is enqueued next."""
+        self._pending_stats = ops.beam_stats_async(self.x, self.z, self.pz)
+
+    @property
+    def stats(self):
+        """The 16 doubles of `dfcsr_beam_stats` for the current particle state (blocks until they have arrived)."""
+        return self._pending_stats.get()
+
+    _sigma_x = property(lambda self: float(self.stats[_lib.S_SIGMA_X]))
+    _sigma_z = property(lambda self: float(self.stats[_lib.S_SIGMA_Z]))
+    _slope = property(lambda self: np.array([self.stats[_lib.S_SLOPE], self.stats[_lib.S_INTERCEPT]]))
+    _mean_x = property(lambda self: float(self.stats[_lib.S_MEAN_X]))
+    _mean_z = property(lambda self: float(self.stats[_lib.S_MEAN_Z]))
 
     def track(self, element, step_size, update_step=True):
         """beams.py:101-106.  `element` comes from tracking.make_element: a Bmad-X element when that package is

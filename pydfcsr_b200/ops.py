@@ -43,20 +43,42 @@ def _stream() -> C.c_void_p:
 _stats_ws: dict = {}
 
 
-def beam_stats(x: torch.Tensor, z: torch.Tensor, pz: torch.Tensor | None = None) -> np.ndarray:
-    """Device reductions -> 16 doubles on the host (indices: ``_lib.S_*``).  Synchronises."""
+class PendingStats:
+    """Result of an asynchronous statistics pass: `get()` waits for the device (once) and returns the 16 doubles."""
+
+    def __init__(self, host_buf, event):
+        self._buf, self._event, self._value = host_buf, event, None
+
+    def get(self) -> np.ndarray:
+        if self._value is None:
+            self._event.synchronize()
+            self._value = self._buf.numpy().copy()
+            self._buf = None
+        return self._value
+
+
+def beam_stats_async(x: torch.Tensor, z: torch.Tensor, pz: torch.Tensor | None = None) -> PendingStats:
+    """Device reductions -> 16 doubles (indices: ``_lib.S_*``) copied to pinned host memory on the current stream.
+    Nothing blocks here: the host can keep enqueueing work and call ``.get()`` when it needs the numbers."""
     _ptr(x), _ptr(z)          # raises for non-CUDA tensors before anything is allocated
     dev = x.device
     if dev not in _stats_ws:
-        _stats_ws[dev] = (torch.zeros(lib.dfcsr_beam_stats_workspace(), dtype=torch.uint8, device=dev),
+        _stats_ws[dev] = [torch.zeros(lib.dfcsr_beam_stats_workspace(), dtype=torch.uint8, device=dev),
                           torch.zeros(_lib.STATS_DOUBLES, dtype=F64, device=dev),
-                          torch.zeros(_lib.STATS_DOUBLES, dtype=F64).pin_memory())
-    ws, d_stats, h_stats = _stats_ws[dev]
+                          [torch.zeros(_lib.STATS_DOUBLES, dtype=F64).pin_memory() for _ in range(8)], 0]
+    ws, d_stats, pool, k = _stats_ws[dev]
+    _stats_ws[dev][3] = (k + 1) % len(pool)      # eight results may be in flight before a pinned buffer is reused
     check(lib.dfcsr_beam_stats(_ptr(_f64(x, "x")), _ptr(_f64(z, "z")), _ptr(pz), x.numel(), _ptr(d_stats),
                                _ptr(ws), _stream()), "dfcsr_beam_stats")
-    h_stats.copy_(d_stats, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
-    return h_stats.numpy().copy()
+    pool[k].copy_(d_stats, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    return PendingStats(pool[k], ev)
+
+
+def beam_stats(x: torch.Tensor, z: torch.Tensor, pz: torch.Tensor | None = None) -> np.ndarray:
+    """Device reductions -> 16 doubles on the host (indices: ``_lib.S_*``).  Synchronises."""
+    return beam_stats_async(x, z, pz).get()
 
 
 _cov_ws: dict = {}
