@@ -266,8 +266,9 @@ def gpu_arm(args):
     out_host = [torch.empty_like(host[1]).pin_memory(), torch.empty_like(host[5]).pin_memory(),
                 torch.empty((2, csr.CSR_params.xbins, csr.CSR_params.zbins), dtype=torch.float64).pin_memory()]
     k4_events = []
+    k4_e2e_events = []          # K4 inside the pipelined end-to-end loop (copies in flight on the second stream)
 
-    def hot_path(timed_k4):
+    def hot_path(timed_k4, sink=None):
         beam.update_status()
         b = beam
         trk.get_DF(x=b.x, z=b.z, px=b.px, t=b.position, stats=b.stats)
@@ -285,7 +286,7 @@ def gpu_arm(args):
             csr.calculate_2D_CSR()
         if timed_k4:
             ev[1].record()
-            k4_events.append(ev)
+            (k4_events if sink is None else sink).append(ev)
         b.apply_wakes(csr.dE_dct, csr.x_kick, csr.CSR_xrange_transformed, csr.CSR_zrange, 0.1, 1)
         trk.pop_right_interpolant()
 
@@ -335,7 +336,7 @@ def gpu_arm(args):
                                        # stream it is ordered after the download of step i-1 from that buffer
             main_stream.wait_event(up[b])
             beam.coords = dbuf[b]
-            hot_path(False)
+            hot_path(True, k4_e2e_events)
             res = (csr.dE_dct, csr.x_kick)
             done[b].record(main_stream)
             with torch.cuda.stream(copy_stream):
@@ -380,6 +381,7 @@ def gpu_arm(args):
     ms_e2e_serial = timed(step_e2e, args.steps)
     e2e_pipelined(3)
     barrier()
+    k4_e2e_events.clear()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     e2e_pipelined(args.steps)
@@ -429,6 +431,7 @@ def gpu_arm(args):
                                     if getattr(csr, "_peer_grid", None) is not None else "NCCL all-gather"))
                    if parallel else "single GPU"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "k4_ms_per_launch": float(np.mean([a.elapsed_time(b) for a, b in k4_e2e_events])) if k4_e2e_events else None,
                 "ms_per_step_unpipelined": ms_e2e_serial / args.steps,
                 "how": "per step: x, px, z, pz H2D from pinned host memory, hot path, px, pz and both wake grids D2H; "
                        "copies double-buffered on a second stream (the unpipelined figure serialises them)",
