@@ -316,15 +316,16 @@ def gpu_arm(args):
         for k in (2, 3):
             dbuf[b][k].copy_(pristine[k])
 
-    def e2e_pipelined(steps):
+    def e2e_pipelined(steps, diag=""):
         up = [torch.cuda.Event() for _ in range(2)]
         done = [torch.cuda.Event() for _ in range(2)]
         saved = beam.coords
 
         def upload(b):
             with torch.cuda.stream(copy_stream):
-                for k in (0, 1, 4, 5):
-                    dbuf[b][k].copy_(host[k], non_blocking=True)
+                if diag not in ("nocopy", "noup"):
+                    for k in (0, 1, 4, 5):
+                        dbuf[b][k].copy_(host[k], non_blocking=True)
                 up[b].record(copy_stream)
 
         upload(0)
@@ -341,6 +342,8 @@ def gpu_arm(args):
             done[b].record(main_stream)
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(done[b])
+                if diag in ("nocopy", "nodown"):
+                    continue
                 out_host[0].copy_(dbuf[b][1], non_blocking=True)
                 out_host[1].copy_(dbuf[b][5], non_blocking=True)
                 out_host[2][0].copy_(res[0], non_blocking=True)
@@ -391,6 +394,14 @@ def gpu_arm(args):
     if parallel:
         dist.all_reduce(ms_pipe, op=dist.ReduceOp.MAX)
     ms_e2e = float(ms_pipe[0])
+    if os.environ.get("DFCSR_BENCH_E2E_DIAG") and rank == 0:      # developer diagnostic: which copies cost what
+        for mode in ("nocopy", "noup", "nodown", ""):
+            e2e_pipelined(3, mode)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e2e_pipelined(args.steps, mode)
+            torch.cuda.synchronize()
+            print(f"[bench diag] pipelined loop, {mode or 'all copies'}: {(time.perf_counter() - t0) / args.steps * 1e3:.3f} ms per step", file=sys.stderr)
     clocks = sampler.stop() if sampler else None
 
     ms_step = ms_total / args.steps

@@ -130,6 +130,12 @@ int64_t dfcsr_beam_stats_workspace(void);
 int dfcsr_beam_stats(const double* d_x, const double* d_z, const double* d_pz, int64_t n,
                      double* d_stats, void* d_workspace, void* stream);
 
+/* n doubles from device memory into PINNED host memory (cudaHostAlloc / cudaHostRegister, mapped), stored by a one-warp
+ * kernel instead of the device-to-host copy engine, so that a small result the host is waiting for (the 16 statistics
+ * of dfcsr_beam_stats) does not queue behind a bulk download running on another stream.  Visible to the host once an
+ * event recorded after it on `stream` has completed.  Fails with DFCSR_ERR_CUDA if h_dst is not mapped pinned memory. */
+int dfcsr_mirror_to_host(const double* d_src, double* h_dst, int32_t n, void* stream);
+
 /* ---- 6 x 6 phase-space covariance (twiss.py:2-71: np.cov([x, px, pz]) and np.cov([y, py, pz]) per step,
  * CSR.py:837-859) -- one read of the six coordinate arrays, deterministic reduction.
  * d_out[27]: means of (x, px, y, py, z, pz), then the upper triangle (i <= j, row-major) of the covariance

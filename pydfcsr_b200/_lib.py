@@ -64,6 +64,7 @@ SIGNATURES = {
     "dfcsr_launch_count": (_L, []),
     "dfcsr_beam_stats_workspace": (_L, []),
     "dfcsr_beam_stats": (C.c_int, [_P, _P, _P, _L, _P, _P, _P]),
+    "dfcsr_mirror_to_host": (C.c_int, [_P, _P, _I, _P]),
     "dfcsr_beam_cov_workspace": (_L, []),
     "dfcsr_beam_cov": (C.c_int, [_P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
     "dfcsr_deposit_cic": (C.c_int, [_P, _P, _P, _L, _I, _D, _D, _I, _D, _D, _P, _P, _I, _P]),

@@ -347,3 +347,27 @@ extern "C" int dfcsr_apply_kick(const double* d_x, const double* d_z, double* d_
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;
 }
+
+// ---- small results to pinned host memory without the copy engine ---------------------------------------------
+// The 16 statistics of a pass are what the host waits for between two steps.  Sent with cudaMemcpyAsync they queue on the
+// device-to-host copy engine behind any bulk download in flight on another stream (measured: +0.15 ms per step in the
+// end-to-end loop of bench.py, whose 16 MB result download runs concurrently).  A one-warp kernel that stores them
+// straight into mapped pinned memory does not.
+__global__ void mirror_kernel(const double* __restrict__ src, double* __restrict__ dst, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+
+extern "C" int dfcsr_mirror_to_host(const double* d_src, double* h_dst, int32_t n, void* stream) {
+    DFCSR_REQUIRE(d_src && h_dst && n > 0, "bad argument");
+    double* mapped = nullptr;
+    const cudaError_t e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&mapped), h_dst, 0);
+    if (e != cudaSuccess) {
+        cudaGetLastError();      // not sticky: clear it so that the caller's fallback (cudaMemcpyAsync) starts clean
+        return cuda_fail(e, "cudaHostGetDevicePointer (h_dst must be mapped pinned memory)");
+    }
+    mirror_kernel<<<1, 32, 0, as_stream(stream)>>>(d_src, mapped, n);
+    count_launch(1);
+    DFCSR_CUDA_OK(cudaGetLastError());
+    return DFCSR_OK;
+}

@@ -6,6 +6,7 @@ hand-written sm_100a kernels in ``csrc/``.  There is no CPU fallback: a non-CUDA
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -43,6 +44,10 @@ def _stream() -> C.c_void_p:
 _stats_ws: dict = {}
 
 
+# DFCSR_STATS_MIRROR=1: deliver the statistics with dfcsr_mirror_to_host (no copy engine) instead of cudaMemcpyAsync
+_mirror_ok = os.environ.get("DFCSR_STATS_MIRROR", "0") == "1"
+
+
 class PendingStats:
     """Result of an asynchronous statistics pass: `get()` waits for the device (once) and returns the 16 doubles."""
 
@@ -70,7 +75,11 @@ def beam_stats_async(x: torch.Tensor, z: torch.Tensor, pz: torch.Tensor | None =
     _stats_ws[dev][3] = (k + 1) % len(pool)      # eight results may be in flight before a pinned buffer is reused
     check(lib.dfcsr_beam_stats(_ptr(_f64(x, "x")), _ptr(_f64(z, "z")), _ptr(pz), x.numel(), _ptr(d_stats),
                                _ptr(ws), _stream()), "dfcsr_beam_stats")
-    pool[k].copy_(d_stats, non_blocking=True)
+    global _mirror_ok
+    if _mirror_ok:      # one-warp store into the mapped pinned buffer: no copy engine, nothing to queue behind
+        _mirror_ok = lib.dfcsr_mirror_to_host(_ptr(d_stats), C.c_void_p(pool[k].data_ptr()), _lib.STATS_DOUBLES, _stream()) == 0
+    if not _mirror_ok:
+        pool[k].copy_(d_stats, non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()
     return PendingStats(pool[k], ev)
