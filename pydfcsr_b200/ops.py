@@ -44,8 +44,9 @@ def _stream() -> C.c_void_p:
 _stats_ws: dict = {}
 
 
-# DFCSR_STATS_MIRROR=1: deliver the statistics with dfcsr_mirror_to_host (no copy engine) instead of cudaMemcpyAsync
-_mirror_ok = os.environ.get("DFCSR_STATS_MIRROR", "0") == "1"
+# the statistics travel through dfcsr_mirror_to_host (no copy engine); DFCSR_STATS_MIRROR=0 or a failing call (pinned
+# memory not mapped) falls back to cudaMemcpyAsync
+_mirror_ok = os.environ.get("DFCSR_STATS_MIRROR", "1") != "0"
 
 
 class PendingStats:
