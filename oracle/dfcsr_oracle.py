@@ -754,3 +754,89 @@ def twiss_from_coords(coords, p0c, mc2):
                 "eta": qd / d2, "etap": pd / d2, "norm_emit": emit * p0c / mc2}
         out.update({f"{k}_{plane}": v for k, v in vals.items()})
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# Zero-density skipping of the CUDA wake kernel, as an executable specification (no reference
+# counterpart: the reference evaluates every sample; every term of its integrands carries rho' or
+# grad rho' (CSR.py:732-775), so samples whose eight voxels hold none add exactly 0).
+# tests/ check (i) that property on the unmodified reference, (ii) that the rules below never drop a
+# sample that can contribute, on many geometries; the GPU tests check the kernel bitwise.
+# --------------------------------------------------------------------------------------------
+def row_support(hist: HistoryStack):
+    """(T, X, 2) int array: per slice and transverse row the hull [z_lo, z_hi] of the voxels with non-zero
+    density, d(density)/dx or d(density)/dz; (INT32_MAX, -1) for an empty row (dfcsr_history_row_support)."""
+    nzv = (hist.data["density"] != 0) | (hist.data["density_x"] != 0) | (hist.data["density_z"] != 0)
+    T, X, Z = nzv.shape
+    rows = nzv.any(axis=2)
+    lo = np.where(rows, nzv.argmax(axis=2), np.iinfo(np.int32).max)
+    hi = np.where(rows, Z - 1 - nzv[:, :, ::-1].argmax(axis=2), -1)
+    return np.stack([lo, hi], axis=2).astype(np.int64)
+
+
+def skip_plan(s, x, xp, s_lo, s_hi, n_s, sc: WakeScalars, lat: LatticeTables, hist: HistoryStack, support=None):
+    """What the kernel does for ONE x' node of one rectangle (wake.cu, kSupport path).  Returns
+    (swept, gathered): boolean arrays over the n_s s' nodes -- `swept` = nodes inside the 32-node blocks the
+    coarse bracket keeps, `gathered` = swept nodes that pass the exact in-grid test and the per-slice hull test."""
+    T, X, Z = hist.shape
+    sup = row_support(hist) if support is None else support
+    sn = np.linspace(s_lo, s_hi, n_s)
+    gathered = np.zeros(n_s, bool)
+    swept = np.zeros(n_s, bool)
+    uy = (xp - hist.min_y) / hist.delta_y
+    if not (uy > -1 and uy < X):
+        return swept, gathered
+    y0 = int(uy)
+    y1 = y0 if y0 == X - 1 else y0 + 1
+
+    def orbit(q, tab):
+        return interp1d(q, tab, lat.min_s, lat.delta_s)
+    obs = np.array([s])
+    cx = orbit(obs, lat.coords[:, 0])[0] - orbit(sn, lat.coords[:, 0]) + x * orbit(obs, lat.n_vec[:, 0])[0]
+    cy = orbit(obs, lat.coords[:, 1])[0] - orbit(sn, lat.coords[:, 1]) + x * orbit(obs, lat.n_vec[:, 1])[0]
+    rx, ry = cx - xp * orbit(sn, lat.n_vec[:, 0]), cy - xp * orbit(sn, lat.n_vec[:, 1])
+    t_ret = sc.t - np.sqrt(rx ** 2 + ry ** 2)
+    ut = (t_ret - hist.min_x) / hist.delta_x
+    uz = ((sn - t_ret) - hist.min_z) / hist.delta_z
+    # per-slice pair hulls of the two rows: {lo - 1, hi} for cell t0 = hull(t0) U hull(t0 + 1)
+    cell = np.empty((T, 2), np.int64)
+    for t in range(T):
+        t1 = t if t == T - 1 else t + 1
+        lo = min(sup[t, y0, 0], sup[t, y1, 0], sup[t1, y0, 0], sup[t1, y1, 0])
+        hi = max(sup[t, y0, 1], sup[t, y1, 1], sup[t1, y0, 1], sup[t1, y1, 1])
+        cell[t] = (lo - 1 if lo != np.iinfo(np.int32).max else lo, hi)
+    band_lo, band_hi = cell[:, 0].min(), cell[:, 1].max()
+    # coarse pass: 32 samples spread over the rectangle, classes below / near / above the band
+    m = (n_s + 31) >> 5
+    jc = np.minimum(np.arange(32) * m, n_s - 1)
+    kmax = float(np.max(np.abs(lat.rho))) if len(lat.rho) else 0.0
+    step = abs(s_hi - s_lo) / (n_s - 1) if n_s > 1 else 0.0
+    delta = 2.0 + 2.0 * m * step * abs(xp) * kmax / hist.delta_z
+    cuz = uz[jc]
+    cls = np.zeros(32, np.int64)
+    with np.errstate(invalid="ignore"):
+        cls[(band_lo > band_hi) | (cuz < band_lo - delta)] = 1
+        cls[(cls == 0) & (cuz >= band_hi + 1.0 + delta)] = 2
+    j_lo, j_hi = 0, n_s - 1
+    lead = 0
+    if cls[0] != 0:
+        while lead < 32 and cls[lead] == cls[0]:
+            lead += 1
+    trail = 0
+    if cls[31] != 0:
+        while trail < 32 and cls[31 - trail] == cls[31]:
+            trail += 1
+    if lead == 32:
+        return swept, gathered
+    if lead > 0:
+        j_lo = max(j_lo, min((lead - 1) * m, n_s - 1) & ~31)
+    if trail > 0:
+        j_hi = min(j_hi, min((32 - trail) * m, n_s - 1))
+    for j0 in range(j_lo, j_hi + 1, 32):
+        swept[j0:j0 + 32] = True
+    with np.errstate(invalid="ignore"):
+        inside = (ut > -1) & (ut < T) & (uz > -1) & (uz < Z)
+    t0 = np.where(inside, ut, 0).astype(np.int64)
+    z0 = np.where(inside, uz, 0).astype(np.int64)
+    gathered = swept & inside & (z0 >= cell[t0, 0]) & (z0 <= cell[t0, 1])
+    return swept, gathered

@@ -202,3 +202,31 @@ def test_gpu_sgolay2d_golden():
         assert _rel(col.cpu().numpy(), g[f"col_{window}_{order}"]) < 1e-13
         assert _rel(row.cpu().numpy(), g[f"row_{window}_{order}"]) < 1e-13
         assert _rel(ops.sgolay2d(dz, window, order, "row").cpu().numpy(), g[f"row_{window}_{order}"]) < 1e-13
+
+
+@pytest.mark.parametrize("tilt,n_bend_steps", [(0.0, 4), (2.5, 4), (-2.5, 4), (2.5, 2), (-1.2, 3)])
+def test_skip_plan_never_drops_a_contributing_sample(tilt, n_bend_steps):
+    """The zero-density skipping rules of the wake kernel, restated in the oracle (row hulls + coarse s' bracket per
+    x' node): over every rectangle of several observation points, a sample the plan does not gather must be one
+    whose integrands are exactly zero in the full evaluation."""
+    sc = scenario.chicane_entry(tilt=tilt, n_bend_steps=n_bend_steps)
+    hs, lat = sc["stack"], sc["lattice"]
+    osc = O.WakeScalars(nx=24, nz=70, **sc["wake_scalars"])
+    sup = O.row_support(hs)
+    ws = sc["wake_scalars"]
+    skipped = total = 0
+    for dz, dx in ((0.4, 0.3), (-2.0, 1.5), (2.5, -2.0)):
+        s_obs = sc["pos"] + dz * ws["sigma_z"]
+        x_obs = dx * ws["sigma_x"] + ws["slope0"] * dz * ws["sigma_z"]
+        for (xa, xb, n_x, sa, sb, n_s) in O.wake_regions(s_obs, x_obs, osc):
+            xn, sn = np.linspace(xa, xb, n_x), np.linspace(sa, sb, n_s)
+            xm, sm = np.meshgrid(xn, sn, indexing="ij")
+            with np.errstate(all="ignore"):
+                iz, ix = O.wake_integrand(s_obs, x_obs, osc, lat, hs, xm.ravel(), sm.ravel())
+            contributes = ((iz != 0) | (ix != 0)).reshape(n_x, n_s)
+            for i in range(n_x):
+                swept, gathered = O.skip_plan(s_obs, x_obs, xn[i], sa, sb, n_s, osc, lat, hs, support=sup)
+                assert not np.any(contributes[i] & ~gathered), (tilt, dz, dx, i)
+                skipped += int((~gathered).sum())
+                total += n_s
+    assert 0 < skipped < total
