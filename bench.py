@@ -34,6 +34,10 @@ _JSON_OUT = sys.stdout
 METRIC = "csr_wake_obs_points_x_integrand_samples_per_s"
 UNIT = "point-samples/s"
 
+PORT_NOTE = ("oracle port of get_CSR_wake (numpy temporaries + numba gathers, the reference's structure); per point it is about "
+             "1.2x FASTER than the unmodified reference (39.7 vs 48.2 ms at 200x200, measured in the build container against "
+             "/root/reference, which does not exist on the GPU box), so GPU/CPU ratios against it are conservative")
+
 WORKLOAD = dict(
     name="chicane_1e6_mesh64x64_int200x200_fp64",
     n_particle=1_000_000, seed=0, position=0.6,
@@ -148,7 +152,7 @@ def cpu_wake_sample(xm, zm, sc, lat, hist, indices, cores, repeats=1):
 def oracle_state(wl):
     """Build the bench state (history at 0.6 m, mesh, scalars) with the CPU oracle only."""
     from oracle import dfcsr_oracle as O
-    from pydfcsr_b200 import synth, tracking
+    from pydfcsr_b200 import synth, tracking          # pure-host modules: the CUDA library is not loaded by these
     cfg = O.DepositConfig(**wl["deposition"])
     hist = O.HistoryOracle(cfg)
     coords = tuple(synth.gaussian_bunch(wl["n_particle"], seed=wl["seed"]))
@@ -207,7 +211,10 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wl = WORKLOAD
+    wl = dict(WORKLOAD)
+    if args.gpus > 1:                       # same weak-scaling mesh and workload name as the GPU arm at this N
+        wl["mesh"] = dict(wl["mesh"], zbins=wl["mesh"]["zbins"] * args.gpus)
+        wl["name"] = wl["name"].replace("mesh64x64", f"mesh{wl['mesh']['xbins']}x{wl['mesh']['zbins']}")
     cores = os.cpu_count() or 1
     xm, zm, sc, lat, hist = oracle_state(wl)
     n = len(xm)
@@ -228,7 +235,7 @@ def reference_arm(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["name"], "mesh": [wl["mesh"]["xbins"], wl["mesh"]["zbins"]], "integration": [sc.nx, sc.nz],
                        "n_particle": wl["n_particle"], "history": list(hist.shape)},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "kind_note": PORT_NOTE, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=_JSON_OUT, flush=True)
 
@@ -408,6 +415,8 @@ def gpu_arm(args):
     value = n_pts * spp / (ms_step * 1e-3)
     e2e_value = n_pts * spp / (ms_e2e / args.steps * 1e-3)
 
+    # ---- parity on every line (all ranks take part: the parallel launch is collective) -----------------------------------
+    hot_state = _final_state(csr, trk, O, pristine, parallel)
     if rank != 0:
         return
     peaks = {}
@@ -415,25 +424,38 @@ def gpu_arm(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     # 5 fields x 8 corners x 8 B per in-grid sample; 4 B in the optional fp32-storage mode
     k4_bytes = (320.0 if args.precision == "fp64" else 160.0) * n_gat_local
     traffic = None                      # DRAM bytes per K4 launch from the committed ncu --set full capture
+    traffic_src = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "k4_ncu_traffic.json")))
-        if world == 1 and args.precision == "fp64":
+        if args.precision == "fp64":
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            traffic_src = tr.get("source")
     except Exception:
         pass
     achieved = k4_bytes / (k4_ms * 1e-3) / 1e9
+    # The unit that bounds K4 is the L1 -> register load path (the 96 MB stack is L2-resident, DRAM traffic ~0.2 % of
+    # peak): the peak is measured on this GPU by tools/l1_probe.cu; without the probe binary, nominal 128 B/clk/SM.
+    sm_mhz = float((clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0)
+    if probe:
+        l1_peak = max(probe["l1_broadcast_gbs"], probe["l1_contiguous_gbs"])
+        l1_src = "tools/l1_probe.cu on this GPU at process start: 16-byte loads from an L1-resident window"
+    else:
+        l1_peak = 148 * 128 * sm_mhz * 1e6 / 1e9
+        l1_src = "nominal 148 SMs x 128 B/clk x max SM clock (probe binary absent)"
+    mesh_now = [csr.CSR_params.xbins, csr.CSR_params.zbins]
+    wl_name = wl["name"] if world == 1 else wl["name"].replace("mesh64x64", f"mesh{mesh_now[0]}x{mesh_now[1]}")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "s_per_lattice_step": ms_step * 1e-3,
         "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["name"], "mesh": [csr.CSR_params.xbins, csr.CSR_params.zbins],
+        "config": {"workload": wl_name, "mesh": mesh_now,
                    "integration": [wp.nx, wp.nz], "n_particle": wl["n_particle"],
-                   "history": [trk.history.T + 1, trk._ring.shape[1], trk._ring.shape[2]],
+                   "history": list(hot_state["hist"].shape),
                    "samples_per_point": spp, "position_m": wl["position"],
                    "l2": "256 MiB device memset between steps (inside the timed region)",
                    "points_per_gpu": n_pts // world,
@@ -450,46 +472,55 @@ def gpu_arm(args):
                 "d2h_bytes_per_step": int(out_host[0].numel() * 8 * 2 + out_host[2].numel() * 8)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "wake_mesh_kernel_p (K4)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+        "roofline": {"bound": "l1", "kernel": "wake_mesh_kernel_p (K4)", "achieved": achieved, "peak": l1_peak,
+                     "unit": "GB/s", "frac": achieved / l1_peak, "traffic": traffic,
+                     "peak_source": l1_src, "traffic_source": traffic_src,
+                     "hbm_actual": {"frac": (traffic / (k4_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None, "peak": hbm_peak,
+                                    "unit": "GB/s", "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                                    "how": "DRAM bytes per launch (ncu) / K4 launch time / measured HBM copy peak: the history "
+                                           "stack is L2-resident, HBM does not bind this kernel at this configuration"},
                      "k4_ms_per_launch": k4_ms, "k4_share_of_step": k4_ms / ms_step,
                      "in_grid_samples_per_launch": n_in_local, "in_grid_fraction": n_in_local / (n_pts * spp / world),
                      "gathered_samples_per_launch": n_gat_local,
-                     "note": "algorithmic bytes = 320 B per in-grid integrand sample that is actually gathered (samples whose eight voxels "
-                             "carry no density are skipped via the row-support table and count 0 B): gather traffic served by L1/L2 "
-                             "(stack footprint << bytes), so frac can exceed 1 against the HBM copy peak; what binds is "
-                             "instruction issue with half-rate fp64 plus the L1 load path (see DESIGN.md, profiles/)"},
+                     "note": "achieved = algorithmic gather bytes (320 B per in-grid integrand sample that is actually gathered; "
+                             "samples whose eight voxels carry no density are skipped via the row-support table and count 0 B) / "
+                             "K4 launch time; this traffic is served by L1/L2, so the roofline is the L1 load path, not HBM "
+                             "(DESIGN.md §4, profiles/)"},
+        "parity": hot_state["parity"],
     }
     if probe:
-        l1_peak = max(probe["l1_broadcast_gbs"], probe["l1_contiguous_gbs"])
-        line["roofline"]["l1_gather"] = {"achieved": achieved, "peak": l1_peak, "unit": "GB/s", "frac": achieved / l1_peak,
-                                         "how": "peak = 16-byte loads from an L1-resident window, tools/l1_probe.cu, same GPU, "
-                                                "same process start; achieved = same algorithmic bytes as above", "probe": probe}
+        line["roofline"]["probe"] = probe
     if args.precision != "fp64":
         line["dtype"] = "f64 math, f32 history storage (optional mode, wakes within 1e-4)"
         line["config"]["workload"] += "_" + args.precision + "_history"
+    cores = os.cpu_count() or 1
+    n_all = len(hot_state["xm"])
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        # identical inputs for the checker: export the device history (7 slices) to the host
-        hot_state = _export_state(csr, trk, O, pristine)
-        per_core = args.cpu_points_per_core
-        idx = np.linspace(0, n_pts - 1, min(n_pts, cores * per_core)).astype(np.int64)
-        de, kick, sec = cpu_wake_sample(hot_state["xm"], hot_state["zm"], hot_state["sc"], hot_state["lat"],
-                                        hot_state["hist"], idx, cores)
-        g_de = hot_state["gpu_de"][idx]
-        g_kick = hot_state["gpu_kick"][idx]
-        line["cpu_baseline"] = {"value": len(idx) * spp / sec, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{len(idx)} of {n_pts} mesh points (evenly spaced) x {spp} samples, wake stage "
+        n_chk = min(n_all, cores * args.cpu_points_per_core)
+    else:
+        n_chk = min(n_all, 64)                      # N > 1: the parity check only (>= 64 evenly spaced points of the gathered grid)
+    idx = np.linspace(0, n_all - 1, n_chk).astype(np.int64)
+    de, kick, sec = cpu_wake_sample(hot_state["xm"], hot_state["zm"], hot_state["sc"], hot_state["lat"],
+                                    hot_state["hist"], idx, min(cores, n_chk))
+    g_de, g_kick = hot_state["gpu_de"][idx], hot_state["gpu_kick"][idx]
+    line["parity"].update({"points_checked": int(n_chk), "checker": "oracle port (CPU), same history exported from the device",
+                           "max_rel_dE": float(np.max(np.abs(g_de - de)) / np.max(np.abs(de))),
+                           "max_rel_kick": float(np.max(np.abs(g_kick - kick)) / np.max(np.abs(kick))), "gate": 1e-10})
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = {"value": len(idx) * spp / sec, "unit": UNIT, "cores": cores, "kind": "port", "kind_note": PORT_NOTE,
+                                "sample": f"{len(idx)} of {n_all} mesh points (evenly spaced) x {spp} samples, wake stage "
                                           f"only, {cores} fork workers, {sec:.2f} s",
-                                "parity_max_rel_dE": float(np.max(np.abs(g_de - de)) / np.max(np.abs(de))),
-                                "parity_max_rel_kick": float(np.max(np.abs(g_kick - kick)) / np.max(np.abs(kick)))}
+                                "parity_max_rel_dE": line["parity"]["max_rel_dE"],
+                                "parity_max_rel_kick": line["parity"]["max_rel_kick"]}
     print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
-def _export_state(csr, trk, O, pristine):
-    """Host copies of exactly what the last GPU wake launch consumed (history incl. the 0.6 m slice)."""
+def _final_state(csr, trk, O, pristine, parallel):
+    """Host copies of exactly what a GPU wake launch of the timed step consumes (history incl. the 0.6 m slice), plus the
+    wake grids of that launch.  Collective: with N > 1 every rank runs the sharded launch (K4 + exchange) and then the whole
+    mesh by itself; rank 0 reports whether the gathered grid is bitwise the serial one and bitwise equal on all ranks."""
     import torch
+    import torch.distributed as dist
     b = csr.beam
     b.coords[1].copy_(pristine[1]); b.coords[5].copy_(pristine[5])
     # redo deposit + push so that the ring holds the 0.6 m slice, run the wake, export, then restore
@@ -499,17 +530,38 @@ def _export_state(csr, trk, O, pristine):
     trk.append_interpolant(formation_length=csr.formation_length, n_formation_length=csr.integration_params.n_formation_length)
     trk.build_interpolant()
     csr.get_CSR_mesh()
-    csr.calculate_2D_CSR()
+    parity = {}
+    if parallel:
+        csr.calculate_2D_CSR_parallel()
+        par = torch.stack([csr.dE_dct.clone(), csr.x_kick.clone()])
+        csr.calculate_2D_CSR()
+        ser = torch.stack([csr.dE_dct, csr.x_kick])
+        flags = torch.tensor([int(torch.equal(par, ser))], dtype=torch.int32, device=par.device)
+        gathered = [torch.empty_like(par) for _ in range(csr.world_size)]
+        dist.all_gather(gathered, par)
+        flags2 = torch.tensor([int(all(torch.equal(g, par) for g in gathered))], dtype=torch.int32, device=par.device)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        dist.all_reduce(flags2, op=dist.ReduceOp.MIN)
+        parity["gathered_equals_serial_launch_bitwise"] = bool(int(flags[0]))
+        parity["ranks_bitwise_equal"] = bool(int(flags2[0]))
+        parity["grid_checked"] = "the gathered (sharded + exchanged) grid"
+        g = par
+    else:
+        csr.calculate_2D_CSR()
+        g = torch.stack([csr.dE_dct, csr.x_kick])
+        parity["grid_checked"] = "single-GPU launch"
     torch.cuda.synchronize()
-    stacks = {name: getattr(trk, f"data_{name}_interp") for name in O.FIELDS}
-    hist = O.HistoryStack(stacks, trk.min_x, trk.min_y, trk.min_z, trk.delta_x, trk.delta_y, trk.delta_z)
-    lat = O.LatticeTables(csr.lattice.coords, csr.lattice.n_vec, csr.lattice.tau_vec, float(csr.lattice.min_x),
-                          float(csr.lattice.delta_x), csr.lattice.rho, csr.lattice.distance)
-    wp = csr._wake_params()
-    sc = O.WakeScalars(t=wp.t, sigma_x=wp.sigma_x, sigma_z=wp.sigma_z, slope0=wp.slope0, mean_x=wp.mean_x,
-                       formation_window=wp.formation_window, csr_scaling=wp.csr_scaling, nx=wp.nx, nz=wp.nz)
-    out = dict(xm=csr.CSR_xmesh, zm=csr.CSR_zmesh, sc=sc, lat=lat, hist=hist,
-               gpu_de=csr.dE_dct.cpu().numpy().ravel(), gpu_kick=csr.x_kick.cpu().numpy().ravel())
+    out = dict(parity=parity)
+    if csr.rank == 0:
+        stacks = {name: getattr(trk, f"data_{name}_interp") for name in O.FIELDS}
+        hist = O.HistoryStack(stacks, trk.min_x, trk.min_y, trk.min_z, trk.delta_x, trk.delta_y, trk.delta_z)
+        lat = O.LatticeTables(csr.lattice.coords, csr.lattice.n_vec, csr.lattice.tau_vec, float(csr.lattice.min_x),
+                              float(csr.lattice.delta_x), csr.lattice.rho, csr.lattice.distance)
+        wp = csr._wake_params()
+        sc = O.WakeScalars(t=wp.t, sigma_x=wp.sigma_x, sigma_z=wp.sigma_z, slope0=wp.slope0, mean_x=wp.mean_x,
+                           formation_window=wp.formation_window, csr_scaling=wp.csr_scaling, nx=wp.nx, nz=wp.nz)
+        out.update(xm=csr.CSR_xmesh, zm=csr.CSR_zmesh, sc=sc, lat=lat, hist=hist,
+                   gpu_de=g[0].cpu().numpy().ravel(), gpu_kick=g[1].cpu().numpy().ravel())
     trk.pop_right_interpolant()
     return out
 

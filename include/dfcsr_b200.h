@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DFCSR_ABI_VERSION 2
+#define DFCSR_ABI_VERSION 3
 #define DFCSR_VOXEL_DOUBLES 6   /* fp64 voxel: 48 bytes */
 #define DFCSR_VOXEL_FLOATS 8    /* fp32 voxel: 32 bytes {density, density_x, density_z, vx, vx_x, 0, 0, 0} */
 #define DFCSR_LATTICE_DOUBLES 6
@@ -115,7 +115,14 @@ typedef struct dfcsr_wake_params {
     double formation_window;   /* n_formation_length * formation_length              */
     double csr_scaling;        /* 8.98755e3 * charge                                 */
     int32_t nx, nz;            /* integration_params.xbins / zbins                   */
+    int32_t skip_mode;         /* dfcsr_skip_mode: zero-density skipping policy      */
+    int32_t reserved;          /* 0                                                  */
 } dfcsr_wake_params;
+
+/* Zero-density skipping in the wake kernel (needs dfcsr_history.d_row_support; never changes a bit of the result):
+ * AUTO = on when the history grid is sparse by construction (|slope0| > 1, or grid area > 1.5x the +-5 sigma box of the
+ * bunch), where it halves the run time; ON / OFF force it (ON costs ~2-5 % on a bunch that fills its grid). */
+typedef enum { DFCSR_SKIP_AUTO = 0, DFCSR_SKIP_ON = 1, DFCSR_SKIP_OFF = 2 } dfcsr_skip_mode;
 
 int dfcsr_abi_version(void);
 const char* dfcsr_last_error(void);
@@ -185,14 +192,18 @@ int dfcsr_make_df(const double* d_count, const double* d_vxsum, dfcsr_axis x_axi
  * Samples the five fields of one raw density-function record (field stack on src axes) on the
  * history grid and writes one voxel slice.  Out-of-source points get 0, or the fill value for vx_x
  * (np.mean(vx_x), deposit.py:332,384): *d_fill_vx_x when that device pointer is non-NULL (e.g.
- * scalars[4] of dfcsr_make_df, so the host never has to read it back), else fill_vx_x. */
+ * scalars[4] of dfcsr_make_df, so the host never has to read it back), else fill_vx_x.
+ * d_row_support (may be NULL): the slot's row-support table (next entry) is written by the same kernel, from the
+ * voxels it has just computed, instead of re-reading the slice. */
 int dfcsr_history_regrid(const double* d_fields, dfcsr_axis src_x, dfcsr_axis src_z,
                          dfcsr_axis dst_x, dfcsr_axis dst_z, double fill_vx_x, const double* d_fill_vx_x,
-                         int32_t format, void* d_slice, void* stream);
+                         int32_t format, void* d_slice, int32_t* d_row_support, void* stream);
 
 /* Row support of one voxel slice (see dfcsr_history.d_row_support): d_support[X][2] = {z_lo, z_hi} per row, the
- * first and last z index whose density, d(density)/dx or d(density)/dz is not exactly zero (NaN counts as non-zero);
- * {INT32_MAX, -1} for an all-zero row.  Call it after every dfcsr_history_regrid / dfcsr_history_pack of a slot. */
+ * first and last z index whose density, d(density)/dx or d(density)/dz is not exactly zero, or whose vx / d(vx)/dx
+ * is not finite (NaN counts as non-zero: a sample the reference would turn into NaN is never skipped);
+ * {INT32_MAX, -1} for a row without any.  For slices written by dfcsr_history_pack (imported histories);
+ * dfcsr_history_regrid fills the table itself. */
 int dfcsr_history_row_support(const void* d_slice, int32_t X, int32_t Z, int32_t format, int32_t* d_support, void* stream);
 
 /* field stack (5, X, Z) <-> voxel slice (X, Z, 6): import/export of oracle histories in tests */
@@ -230,6 +241,11 @@ int dfcsr_wake_grid_peers(const dfcsr_history* hist, const dfcsr_lattice* lat, c
                           dfcsr_axis x_axis, dfcsr_axis z_axis, double slope, double intercept,
                           int64_t first, int64_t count, const uint64_t* h_peer_grids, int32_t n_peers,
                           unsigned long long* d_counters, void* stream);
+
+/* 1 if the wake launches above would use zero-density skipping for this history and these beam scalars (row-support
+ * table present and the grid sparse by construction: |slope0| > 1, the chirp-band branch of CSR.py:480, or a history
+ * grid more than 1.5x the +-5 sigma box of the current bunch; wp->skip_mode ON / OFF overrides), else 0; < 0 on error. */
+int dfcsr_wake_uses_skipping(const dfcsr_history* hist, const dfcsr_wake_params* wp);
 
 /* get_CSR_wake(s, x, debug=True) (CSR.py:571-572, 599-600): integrands of one point.
  * d_iz / d_ix receive the regions back to back, each (n_x, n_s) row-major like the reference's

@@ -17,8 +17,9 @@ VOXEL_F64, VOXEL_F32 = 0, 1
 LATTICE_DOUBLES = 6
 STATS_DOUBLES = 16
 DF_SCALARS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_PEERS = 8
+SKIP_MODES = {"auto": 0, "on": 1, "off": 2}
 
 # indices of dfcsr_stat
 (S_MEAN_X, S_MEAN_Z, S_SIGMA_X, S_SIGMA_Z, S_SLOPE, S_INTERCEPT, S_MEAN_XT, S_SIGMA_XT,
@@ -49,7 +50,7 @@ class Lattice(C.Structure):
 class WakeParams(C.Structure):
     _fields_ = [("t", C.c_double), ("sigma_x", C.c_double), ("sigma_z", C.c_double), ("slope0", C.c_double),
                 ("mean_x", C.c_double), ("formation_window", C.c_double), ("csr_scaling", C.c_double),
-                ("nx", C.c_int32), ("nz", C.c_int32)]
+                ("nx", C.c_int32), ("nz", C.c_int32), ("skip_mode", C.c_int32), ("reserved", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -71,7 +72,7 @@ SIGNATURES = {
     "dfcsr_deposit_ngp": (C.c_int, [_P, _P, _L, _I, _D, _D, _I, _D, _D, _P, _P]),
     "dfcsr_make_df_workspace": (_L, [_I, _I]),
     "dfcsr_make_df": (C.c_int, [_P, _P, Axis, Axis, _I, _P, _P, _P, _D, _P, _P, _P, _P]),
-    "dfcsr_history_regrid": (C.c_int, [_P, Axis, Axis, Axis, Axis, _D, _P, _I, _P, _P]),
+    "dfcsr_history_regrid": (C.c_int, [_P, Axis, Axis, Axis, Axis, _D, _P, _I, _P, _P, _P]),
     "dfcsr_history_row_support": (C.c_int, [_P, _I, _I, _I, _P, _P]),
     "dfcsr_history_pack": (C.c_int, [_P, _I, _I, _I, _P, _P]),
     "dfcsr_history_unpack": (C.c_int, [_P, _I, _I, _I, _P, _P]),
@@ -81,6 +82,7 @@ SIGNATURES = {
                                   _L, _L, _P, _P, _P, _P]),
     "dfcsr_wake_grid_peers": (C.c_int, [C.POINTER(History), C.POINTER(Lattice), C.POINTER(WakeParams), Axis, Axis, _D, _D,
                                         _L, _L, C.POINTER(C.c_uint64), _I, _P, _P]),
+    "dfcsr_wake_uses_skipping": (C.c_int, [C.POINTER(History), C.POINTER(WakeParams)]),
     "dfcsr_wake_point_debug": (C.c_int, [C.POINTER(History), C.POINTER(Lattice), C.POINTER(WakeParams),
                                          _D, _D, _P, _P, _L, _P, _P, _P]),
     "dfcsr_apply_kick": (C.c_int, [_P, _P, _P, _P, _L, _D, _D, _P, _P, Axis, Axis, _D, _D, _I, _P]),

@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import distributed as dist_utils
-from . import ops, tracking
+from . import _lib, ops, tracking
 from ._lib import Axis
 from .beams import Beam
 from .deposit import DF_tracker
@@ -285,7 +285,7 @@ class CSR2D:
         b, ip = self.beam, self.integration_params
         return ops.wake_params(t=b.position, sigma_x=b._sigma_x, sigma_z=b._sigma_z, slope0=b._slope[0],
                                mean_x=b._mean_x, formation_window=ip.n_formation_length * self.formation_length,
-                               csr_scaling=self.CSR_scaling, nx=ip.xbins, nz=ip.zbins)
+                               csr_scaling=self.CSR_scaling, nx=ip.xbins, nz=ip.zbins, skip=getattr(self, "skip_mode", "auto"))
 
     def calculate_2D_CSR(self):
         """CSR.py:397-418: the whole mesh in one launch; results stay on the device
@@ -309,9 +309,17 @@ class CSR2D:
         peer = getattr(self, "_peer_grid", None)
         if peer is not None:
             grid, ptrs, handle = peer.next()
-            ops.wake_grid_peers(self.DF_tracker.history, lat, self._wake_params(), xa, za, *self._mesh_slope,
-                                first=int(self.displ[self.rank]), count=int(self.count[self.rank]), peer_ptrs=ptrs,
-                                counters=getattr(self, "wake_counters", None))
+            try:
+                ops.wake_grid_peers(self.DF_tracker.history, lat, self._wake_params(), xa, za, *self._mesh_slope,
+                                    first=int(self.displ[self.rank]), count=int(self.count[self.rank]), peer_ptrs=ptrs,
+                                    counters=getattr(self, "wake_counters", None))
+            except _lib.DfcsrError as e:
+                # The launch was refused before anything ran (e.g. a shared-memory or slice-size limit).  Every rank
+                # launches with the same history geometry and scalars, so every rank lands here in the same step:
+                # the switch to the NCCL all-gather below is collective without any extra exchange.
+                self._log(f"fused K4 exchange refused ({e}); using the NCCL all-gather from now on")
+                self._peer_grid = peer = None
+        if peer is not None:
             handle.barrier(channel=0)
             full = grid.clone()          # value semantics like the NCCL path: the mapped grid is rewritten two steps later
         else:

@@ -20,8 +20,8 @@
 
 namespace dfcsr {
 
-constexpr int kRegridCols = 128;   // threads per block = columns (z) per tile
-constexpr int kRegridRows = 4;     // rows (x) per tile
+constexpr int kRegridThreads = 256;   // threads per block; a block owns kRegridRows whole rows and strides along z
+constexpr int kRegridRows = 2;        // rows (x) per block
 
 struct AxisCell {
     int i;
@@ -64,6 +64,18 @@ __device__ __forceinline__ void store_voxel(void* slice, size_t cell, const doub
     }
 }
 
+// Does a voxel count for the row support?  Any non-zero (or NaN) density / density gradient, or a velocity field that is
+// not finite: the reference turns 0 * inf into NaN, so such a sample must be evaluated, not skipped.  In the fp32 format
+// the test is made on the values as stored.
+template <bool kF32>
+__device__ __forceinline__ bool voxel_supports(const double (&v)[5]) {
+    if (kF32) {
+        const float a = (float)v[0], b = (float)v[1], c = (float)v[2], d = (float)v[3], e = (float)v[4];
+        return !(a == 0.f) || !(b == 0.f) || !(c == 0.f) || !isfinite(d) || !isfinite(e);
+    }
+    return !(v[0] == 0.0) || !(v[1] == 0.0) || !(v[2] == 0.0) || !isfinite(v[3]) || !isfinite(v[4]);
+}
+
 template <bool kF32>
 __device__ __forceinline__ void load_voxel(const void* slice, size_t cell, double (&v)[5]) {
     if (kF32) {
@@ -77,45 +89,68 @@ __device__ __forceinline__ void load_voxel(const void* slice, size_t cell, doubl
     }
 }
 
+// One block re-grids kRegridRows whole rows: every thread resolves the source cell of its columns (z), the rows'
+// source cells come from shared memory.  Because a block sees its rows completely, it also knows their row support
+// (hull of the voxels with non-zero density or density gradient, or non-finite velocity fields): one store per row,
+// no second pass over the slice.
 template <bool kF32>
-__global__ void __launch_bounds__(kRegridCols)
+__global__ void __launch_bounds__(kRegridThreads)
 regrid_kernel(const double* __restrict__ src, Axis sx, Axis sz, Axis dx, Axis dz, double fill_vx_x,
-              const double* __restrict__ fill_ptr, void* __restrict__ slice) {
+              const double* __restrict__ fill_ptr, void* __restrict__ slice, int* __restrict__ support) {
     __shared__ AxisCell rows[kRegridRows];
+    __shared__ int hull[kRegridRows][2][kRegridThreads / 32];
     if (fill_ptr) fill_vx_x = __ldg(fill_ptr);
-    const int col = blockIdx.x * kRegridCols + threadIdx.x;
-    const int row0 = blockIdx.y * kRegridRows;
+    const int row0 = blockIdx.x * kRegridRows;
     if (threadIdx.x < kRegridRows && row0 + threadIdx.x < dx.n)
         rows[threadIdx.x] = locate(sx, axis_node(dx, row0 + threadIdx.x));
-    AxisCell cz;
-    cz.i = 0; cz.y = 0.0; cz.outside = 1;
-    if (col < dz.n) cz = locate(sz, axis_node(dz, col));
     __syncthreads();
-    if (col >= dz.n) return;
     const size_t plane = (size_t)sx.n * sz.n;
-    const double wz1 = cz.y, wz0 = __dsub_rn(1.0, cz.y);
     const int rmax = min(kRegridRows, dx.n - row0);
-    for (int r = 0; r < rmax; ++r) {
-        const AxisCell cx = rows[r];
-        double out[5];
-        if (cx.outside || cz.outside) {
-            out[0] = out[1] = out[2] = out[3] = 0.0;
-            out[4] = fill_vx_x;
-        } else {
-            const double wx1 = cx.y, wx0 = __dsub_rn(1.0, cx.y);
-            const size_t o = (size_t)cx.i * sz.n + cz.i;
+    int lo[kRegridRows], hi[kRegridRows];
 #pragma unroll
-            for (int f = 0; f < 5; ++f) {
-                // scipy's evaluate_linear_2d order: ((F * wx) * wz), corners accumulated in sequence
-                const double* p = src + f * plane + o;
-                double v = __dmul_rn(__dmul_rn(__ldg(p), wx0), wz0);
-                v = __dadd_rn(v, __dmul_rn(__dmul_rn(__ldg(p + 1), wx0), wz1));
-                v = __dadd_rn(v, __dmul_rn(__dmul_rn(__ldg(p + sz.n), wx1), wz0));
-                v = __dadd_rn(v, __dmul_rn(__dmul_rn(__ldg(p + sz.n + 1), wx1), wz1));
-                out[f] = v;
+    for (int r = 0; r < kRegridRows; ++r) { lo[r] = INT_MAX; hi[r] = -1; }
+    for (int col = threadIdx.x; col < dz.n; col += kRegridThreads) {
+        const AxisCell cz = locate(sz, axis_node(dz, col));
+        const double wz1 = cz.y, wz0 = __dsub_rn(1.0, cz.y);
+#pragma unroll
+        for (int r = 0; r < kRegridRows; ++r) {
+            if (r >= rmax) break;
+            const AxisCell cx = rows[r];
+            double out[5];
+            if (cx.outside || cz.outside) {
+                out[0] = out[1] = out[2] = out[3] = 0.0;
+                out[4] = fill_vx_x;
+            } else {
+                const double wx1 = cx.y, wx0 = __dsub_rn(1.0, cx.y);
+                const size_t o = (size_t)cx.i * sz.n + cz.i;
+#pragma unroll
+                for (int f = 0; f < 5; ++f) {
+                    // scipy's evaluate_linear_2d order: ((F * wx) * wz), corners accumulated in sequence
+                    const double* p = src + f * plane + o;
+                    double v = __dmul_rn(__dmul_rn(__ldg(p), wx0), wz0);
+                    v = __dadd_rn(v, __dmul_rn(__dmul_rn(__ldg(p + 1), wx0), wz1));
+                    v = __dadd_rn(v, __dmul_rn(__dmul_rn(__ldg(p + sz.n), wx1), wz0));
+                    v = __dadd_rn(v, __dmul_rn(__dmul_rn(__ldg(p + sz.n + 1), wx1), wz1));
+                    out[f] = v;
+                }
             }
+            store_voxel<kF32>(slice, (size_t)(row0 + r) * dz.n + col, out);
+            if (voxel_supports<kF32>(out)) { lo[r] = min(lo[r], col); hi[r] = max(hi[r], col); }
         }
-        store_voxel<kF32>(slice, (size_t)(row0 + r) * dz.n + col, out);
+    }
+    if (!support) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < kRegridRows; ++r) {
+        const int l = __reduce_min_sync(0xffffffffu, lo[r]), h = __reduce_max_sync(0xffffffffu, hi[r]);
+        if (lane == 0) { hull[r][0][warp] = l; hull[r][1][warp] = h; }
+    }
+    __syncthreads();
+    if (threadIdx.x < rmax) {
+        int l = INT_MAX, h = -1;
+        for (int w = 0; w < kRegridThreads / 32; ++w) { l = min(l, hull[threadIdx.x][0][w]); h = max(h, hull[threadIdx.x][1][w]); }
+        support[2 * (row0 + threadIdx.x)] = l;
+        support[2 * (row0 + threadIdx.x) + 1] = h;
     }
 }
 
@@ -153,18 +188,18 @@ using namespace dfcsr;
 
 extern "C" int dfcsr_history_regrid(const double* d_fields, dfcsr_axis src_x, dfcsr_axis src_z,
                                     dfcsr_axis dst_x, dfcsr_axis dst_z, double fill_vx_x,
-                                    const double* d_fill_vx_x, int32_t format, void* d_slice, void* stream) {
+                                    const double* d_fill_vx_x, int32_t format, void* d_slice, int32_t* d_row_support,
+                                    void* stream) {
     DFCSR_REQUIRE(d_fields && d_slice, "null pointer");
     DFCSR_REQUIRE(src_x.n >= 2 && src_z.n >= 2 && dst_x.n >= 1 && dst_z.n >= 1, "axes too short");
     Axis sx = make_axis(src_x.start, src_x.stop, src_x.n), sz = make_axis(src_z.start, src_z.stop, src_z.n);
     Axis dx = make_axis(dst_x.start, dst_x.stop, dst_x.n), dz = make_axis(dst_z.start, dst_z.stop, dst_z.n);
-    dim3 grid((dz.n + kRegridCols - 1) / kRegridCols, (dx.n + kRegridRows - 1) / kRegridRows);
-    DFCSR_REQUIRE(grid.y <= 65535, "destination grid too tall");
+    const unsigned grid = (unsigned)((dx.n + kRegridRows - 1) / kRegridRows);
     DFCSR_REQUIRE(format == DFCSR_VOXEL_F64 || format == DFCSR_VOXEL_F32, "unknown voxel format");
     if (format == DFCSR_VOXEL_F32)
-        regrid_kernel<true><<<grid, kRegridCols, 0, as_stream(stream)>>>(d_fields, sx, sz, dx, dz, fill_vx_x, d_fill_vx_x, d_slice);
+        regrid_kernel<true><<<grid, kRegridThreads, 0, as_stream(stream)>>>(d_fields, sx, sz, dx, dz, fill_vx_x, d_fill_vx_x, d_slice, d_row_support);
     else
-        regrid_kernel<false><<<grid, kRegridCols, 0, as_stream(stream)>>>(d_fields, sx, sz, dx, dz, fill_vx_x, d_fill_vx_x, d_slice);
+        regrid_kernel<false><<<grid, kRegridThreads, 0, as_stream(stream)>>>(d_fields, sx, sz, dx, dz, fill_vx_x, d_fill_vx_x, d_slice, d_row_support);
     count_launch(1);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;
@@ -180,16 +215,9 @@ row_support_kernel(const void* __restrict__ slice, int X, int Z, int* __restrict
     for (int row = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5); row < X; row += warps) {
         int lo = INT_MAX, hi = -1;
         for (int z = lane; z < Z; z += 32) {
-            bool nz;
-            if (kF32) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(slice) + ((size_t)row * Z + z) * (DFCSR_VOXEL_FLOATS / 4));
-                nz = !(v.x == 0.f) || !(v.y == 0.f) || !(v.z == 0.f);
-            } else {
-                const double2* p = reinterpret_cast<const double2*>(slice) + ((size_t)row * Z + z) * (DFCSR_VOXEL_DOUBLES / 2);
-                const double2 a = __ldg(p);
-                const double b = __ldg(reinterpret_cast<const double*>(p + 1));
-                nz = !(a.x == 0.0) || !(a.y == 0.0) || !(b == 0.0);      // NaN counts as non-zero
-            }
+            double v[5];
+            load_voxel<kF32>(slice, (size_t)row * Z + z, v);
+            const bool nz = voxel_supports<kF32>(v);
             if (nz) { lo = min(lo, z); hi = max(hi, z); }
         }
 #pragma unroll

@@ -182,7 +182,7 @@ class DF_tracker:
     def _ensure_ring(self, X, Z, need):
         ring = self._ring
         if ring is None or ring.shape[1] != X or ring.shape[2] != Z or ring.shape[0] < need:
-            cap = max(16, 1 << (max(need, 1) * 2 - 1).bit_length())
+            cap = self._capacity_for(need)
             self._ring = None          # release the old ring before allocating the new one
             self._ring = ops.new_slices((cap, X, Z), self.precision, self.device)
             self._support = ops.new_row_support(cap, X, self.device)
@@ -190,22 +190,33 @@ class DF_tracker:
             return True
         return False
 
+    @staticmethod
+    def _capacity_for(need):
+        """Ring slots for a window of `need` slices: a quarter of headroom (at least 4 slots), not a power of two --
+        a 2000 x 2000 slice is 192 MB, so a 130-slice window must not allocate 512 slots."""
+        need = max(int(need), 1)
+        return max(16, need + max(4, need // 4))
+
     def _grow_ring(self):
-        """Ring full on a non-rebuild push: double the capacity, keep the window order."""
+        """Ring full on a non-rebuild push: enlarge it, keep the window order.  The window is copied as its two
+        contiguous segments (head .. end of the ring, start .. head), so the peak is old ring + new ring."""
         old, T = self._ring, len(self.time_interp) - 1
-        cap = old.shape[0] * 2
+        cap_old = old.shape[0]
+        cap = self._capacity_for(T + 1 + max(4, T // 4))
         new = torch.empty((cap,) + tuple(old.shape[1:]), dtype=old.dtype, device=self.device)
-        idx = (torch.arange(T, device=self.device) + self._head) % old.shape[0]
-        new[:T] = old[idx]
         sup = ops.new_row_support(cap, old.shape[1], self.device)
-        sup[:T] = self._support[idx]
+        first = min(T, cap_old - self._head)                 # slices from head to the end of the old ring
+        new[:first].copy_(old[self._head:self._head + first])
+        sup[:first].copy_(self._support[self._head:self._head + first])
+        if T > first:                                        # the wrapped part
+            new[first:T].copy_(old[:T - first])
+            sup[first:T].copy_(self._support[:T - first])
         self._ring, self._support, self._head = new, sup, 0
 
     def _regrid(self, rec: _Record, idx):
         """Re-grid one logged record into ring slot `idx` and refresh that slot's row support."""
         ops.history_regrid(rec.fields, rec.x_axis, rec.z_axis, self._x_axis_interp, self._z_axis_interp,
-                           rec.scalars[4:5], self._ring[idx])
-        ops.history_row_support(self._ring[idx], self._support[idx])
+                           rec.scalars[4:5], self._ring[idx], self._support[idx])
 
     def append_interpolant(self, formation_length, n_formation_length):
         start_point = max(0, self.end_time - n_formation_length * formation_length)    # deposit.py:313

@@ -109,6 +109,11 @@ def make_peer_wake_grid(n: int, device: torch.device):
     P2P access): the caller then uses the NCCL all-gather.  The decision is collective: all ranks agree."""
     if os.environ.get("DFCSR_FUSED_GATHER", "1") == "0" or dist.get_backend() != "nccl" or device.type != "cuda":
         return None
+    # peer mappings exist inside one NVLink box only: a job that spans hosts (torchrun sets LOCAL_WORLD_SIZE < WORLD_SIZE)
+    # must not even try the symmetric-memory rendezvous, which may hang there instead of raising
+    local = int(os.environ.get("LOCAL_WORLD_SIZE", dist.get_world_size()))
+    if local != dist.get_world_size() or dist.get_world_size() > 8:
+        return None
     ok, grid = 1, None
     try:
         grid = PeerWakeGrid(n, device)

@@ -50,17 +50,32 @@ _mirror_ok = os.environ.get("DFCSR_STATS_MIRROR", "1") != "0"
 
 
 class PendingStats:
-    """Result of an asynchronous statistics pass: `get()` waits for the device (once) and returns the 16 doubles."""
+    """Result of an asynchronous statistics pass: `get()` waits for the device (once) and returns the 16 doubles.
+    The pinned buffer belongs to this object until it has been read (or the object dies); only then does it go back
+    to the free list, so a result that is read late can never be overwritten by a later pass."""
 
-    def __init__(self, host_buf, event):
-        self._buf, self._event, self._value = host_buf, event, None
+    def __init__(self, host_buf, event, free_list):
+        self._buf, self._event, self._value, self._free = host_buf, event, None, free_list
+
+    def _release(self):
+        if self._buf is not None:
+            self._free.append(self._buf)
+            self._buf = None
 
     def get(self) -> np.ndarray:
         if self._value is None:
             self._event.synchronize()
             self._value = self._buf.numpy().copy()
-            self._buf = None
+            self._release()
         return self._value
+
+    def __del__(self):
+        try:
+            if self._buf is not None:
+                self._event.synchronize()      # the device may still be writing into the buffer
+                self._release()
+        except Exception:
+            pass
 
 
 def beam_stats_async(x: torch.Tensor, z: torch.Tensor, pz: torch.Tensor | None = None) -> PendingStats:
@@ -69,21 +84,22 @@ def beam_stats_async(x: torch.Tensor, z: torch.Tensor, pz: torch.Tensor | None =
     _ptr(x), _ptr(z)          # raises for non-CUDA tensors before anything is allocated
     dev = x.device
     if dev not in _stats_ws:
-        _stats_ws[dev] = [torch.zeros(lib.dfcsr_beam_stats_workspace(), dtype=torch.uint8, device=dev),
-                          torch.zeros(_lib.STATS_DOUBLES, dtype=F64, device=dev),
-                          [torch.zeros(_lib.STATS_DOUBLES, dtype=F64).pin_memory() for _ in range(8)], 0]
-    ws, d_stats, pool, k = _stats_ws[dev]
-    _stats_ws[dev][3] = (k + 1) % len(pool)      # eight results may be in flight before a pinned buffer is reused
+        # [0] reduction workspace, [1] free list of pinned result buffers (grown on demand).  Each pass gets its own
+        # device result vector, so two passes in flight on different streams never share one.
+        _stats_ws[dev] = [torch.zeros(lib.dfcsr_beam_stats_workspace(), dtype=torch.uint8, device=dev), []]
+    ws, free = _stats_ws[dev]
+    host = free.pop() if free else torch.zeros(_lib.STATS_DOUBLES, dtype=F64).pin_memory()
+    d_stats = torch.empty(_lib.STATS_DOUBLES, dtype=F64, device=dev)
     check(lib.dfcsr_beam_stats(_ptr(_f64(x, "x")), _ptr(_f64(z, "z")), _ptr(pz), x.numel(), _ptr(d_stats),
                                _ptr(ws), _stream()), "dfcsr_beam_stats")
     global _mirror_ok
     if _mirror_ok:      # one-warp store into the mapped pinned buffer: no copy engine, nothing to queue behind
-        _mirror_ok = lib.dfcsr_mirror_to_host(_ptr(d_stats), C.c_void_p(pool[k].data_ptr()), _lib.STATS_DOUBLES, _stream()) == 0
+        _mirror_ok = lib.dfcsr_mirror_to_host(_ptr(d_stats), C.c_void_p(host.data_ptr()), _lib.STATS_DOUBLES, _stream()) == 0
     if not _mirror_ok:
-        pool[k].copy_(d_stats, non_blocking=True)
+        host.copy_(d_stats, non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()
-    return PendingStats(pool[k], ev)
+    return PendingStats(host, ev, free)
 
 
 def beam_stats(x: torch.Tensor, z: torch.Tensor, pz: torch.Tensor | None = None) -> np.ndarray:
@@ -254,12 +270,16 @@ def new_slices(shape, precision, device) -> torch.Tensor:
     raise ValueError("precision must be 'fp64' or 'fp32'")
 
 
-def history_regrid(fields, src_x: Axis, src_z: Axis, dst_x: Axis, dst_z: Axis, fill_vx_x, slice_out):
-    """fill_vx_x: host float, or a 1-element CUDA tensor (read on the device, no host sync)."""
+def history_regrid(fields, src_x: Axis, src_z: Axis, dst_x: Axis, dst_z: Axis, fill_vx_x, slice_out, support_out=None):
+    """fill_vx_x: host float, or a 1-element CUDA tensor (read on the device, no host sync).  support_out: the slot's
+    (X, 2) int32 row-support table, filled by the same kernel."""
     dev_fill = fill_vx_x if isinstance(fill_vx_x, torch.Tensor) else None
+    if support_out is not None and (support_out.dtype != torch.int32 or tuple(support_out.shape) != (dst_x.n, 2)
+                                    or not support_out.is_contiguous()):
+        raise _lib.DfcsrError("row support must be a contiguous (X, 2) int32 tensor")
     check(lib.dfcsr_history_regrid(_ptr(fields), src_x, src_z, dst_x, dst_z,
                                    0.0 if dev_fill is not None else float(fill_vx_x), _ptr(dev_fill),
-                                   voxel_format(slice_out), _ptr(slice_out), _stream()), "dfcsr_history_regrid")
+                                   voxel_format(slice_out), _ptr(slice_out), _ptr(support_out), _stream()), "dfcsr_history_regrid")
     return slice_out
 
 
@@ -363,9 +383,10 @@ class DeviceHistory:
                    float(delta_z), support)
 
 
-def wake_params(t, sigma_x, sigma_z, slope0, mean_x, formation_window, csr_scaling, nx, nz) -> _lib.WakeParams:
+def wake_params(t, sigma_x, sigma_z, slope0, mean_x, formation_window, csr_scaling, nx, nz, skip="auto") -> _lib.WakeParams:
+    """skip: zero-density skipping policy, 'auto' (on for sparse history grids), 'on' or 'off' (dfcsr_skip_mode)."""
     return _lib.WakeParams(float(t), float(sigma_x), float(sigma_z), float(slope0), float(mean_x),
-                           float(formation_window), float(csr_scaling), int(nx), int(nz))
+                           float(formation_window), float(csr_scaling), int(nx), int(nz), _lib.SKIP_MODES[skip], 0)
 
 
 def wake_mesh(hist: DeviceHistory, lat: DeviceLattice, wp: _lib.WakeParams, xmesh, zmesh, first=0, count=None,
@@ -403,6 +424,15 @@ def wake_grid_peers(hist: DeviceHistory, lat: DeviceLattice, wp: _lib.WakeParams
     check(lib.dfcsr_wake_grid_peers(C.byref(hv), C.byref(lv), C.byref(wp), x_axis, z_axis, float(slope), float(intercept),
                                     int(first), int(count), peer_ptrs, len(peer_ptrs), _ptr(counters), _stream()),
           "dfcsr_wake_grid_peers")
+
+
+def wake_uses_skipping(hist: DeviceHistory, wp: _lib.WakeParams) -> bool:
+    """Whether a wake launch on this history with these beam scalars selects zero-density skipping."""
+    hv = hist.view()
+    rc = lib.dfcsr_wake_uses_skipping(C.byref(hv), C.byref(wp))
+    if rc < 0:
+        check(rc, "dfcsr_wake_uses_skipping")
+    return rc == 1
 
 
 def wake_point_debug(hist: DeviceHistory, lat: DeviceLattice, wp: _lib.WakeParams, s: float, x: float):

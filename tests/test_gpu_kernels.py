@@ -337,17 +337,15 @@ def test_track_linear_kernel_matches_host_maps(dev):
         assert abs(np.linalg.det(m) - 1.0) < 1e-12                                           # symplectic maps
 
 
-# K4 kernel variants (developer knob DFCSR_WAKE_CFG, read per launch): every shipped variant must meet the same
-# gate as the default.  1 = round-1 s'-lane kernel, 10 = x'-lane register-cached kernel, 20 = trimmed s'-lane
-# kernel, 21/25 = two x' nodes per lane (CTA shapes 2x256 / 2x192 threads per SM).
-@pytest.mark.parametrize("cfg", [0, 1, 10, 20, 25, 30, 40, 45, 46])
+# K4 with every zero-density skipping policy (dfcsr_wake_params.skip_mode): each must meet the same gate.
+@pytest.mark.parametrize("skip", ["auto", "on", "off"])
 @pytest.mark.parametrize("tilt", [0.0, 2.5])
-def test_wake_kernel_variants_match_oracle(dev, monkeypatch, cfg, tilt):
+def test_wake_skip_modes_match_oracle(dev, skip, tilt):
     from pydfcsr_b200 import ops
-    monkeypatch.setenv("DFCSR_WAKE_CFG", str(cfg))
     sc = scenario.chicane_entry(tilt=tilt)
-    nx, nz = 50, 45           # odd x' count in the half-width rectangles: the last pair of a region is half empty
+    nx, nz = 50, 45           # odd node counts: the last 32-node block of a rectangle is partly empty
     hist, dlat, wp, osc = _device_problem(sc, dev, nx, nz)
+    wp = ops.wake_params(nx=nx, nz=nz, skip=skip, **sc["wake_scalars"])
     x, z = sc["coords"][0], sc["coords"][4]
     s = sc["scalars"]
     xm, zm, _, _ = O.observation_mesh(x, z, s["slope"], s["sigma_z"], s["mean_z"], 3, 3, 5, 7)
@@ -359,16 +357,73 @@ def test_wake_kernel_variants_match_oracle(dev, monkeypatch, cfg, tilt):
     assert _rel(kick.cpu().numpy(), ref_kick) < TOL
     n_in, n_all, n_gat = (int(v) for v in cnt.cpu())
     assert n_all == xm.size * (4 if abs(tilt) <= 1 else 5) * nx * nz and 0 < n_gat <= n_in < n_all
-    assert n_gat == n_in or cfg in (0, 46)    # only the default kernel skips zero-density samples (46 = forced on)
-    # the in-grid sample count is a property of the quadrature, not of the kernel variant
-    monkeypatch.setenv("DFCSR_WAKE_CFG", "1")
-    cnt1 = torch.zeros(3, dtype=torch.int64, device=dev)
-    ops.wake_mesh(hist, dlat, wp, _up(xm, dev), _up(zm, dev), counters=cnt1)
-    assert int(cnt1[0]) == n_in or (cfg in (0, 46) and n_in < int(cnt1[0]))   # s' nodes outside the density band are not swept
+    uses = ops.wake_uses_skipping(hist, wp)
+    if skip != "auto" or abs(tilt) > 1:
+        assert uses == (skip != "off")          # AUTO: the chirp-band branch (|slope| > 1) always counts as sparse
+    assert n_gat == n_in if not uses else n_gat <= n_in
+    if uses and tilt != 0.0:
+        assert n_gat < n_in                     # the tilted bunch fills a band of its grid only
     # run-to-run bitwise reproducible
-    monkeypatch.setenv("DFCSR_WAKE_CFG", str(cfg))
     de2, kick2 = ops.wake_mesh(hist, dlat, wp, _up(xm, dev), _up(zm, dev))
     assert torch.equal(de, de2) and torch.equal(kick, kick2)
+
+
+def test_skipping_policy_switch_is_bitwise_neutral(dev):
+    """The AUTO policy turns skipping on when the history grid is more than 1.5x the +-5 sigma box of the bunch
+    (wake.cu: wants_skipping).  Straddle that boundary by scaling sigma_x in the wake scalars: the policy must flip,
+    and on each side the wakes must be bitwise those of the other setting forced (skipping never changes a bit)."""
+    import torch
+    from pydfcsr_b200 import ops
+    sc = scenario.chicane_entry(tilt=0.0)
+    st = sc["stack"]
+    hist, dlat, _wp, _ = _device_problem(sc, dev, 40, 40)
+    base = dict(sc["wake_scalars"])
+    area = (st.shape[1] * st.delta_y) * (st.shape[2] * st.delta_z)
+    sx_edge = area / (1.5 * 100.0 * base["sigma_z"])          # grid_area == 1.5 * (10 sx)(10 sz)
+    x, z = sc["coords"][0], sc["coords"][4]
+    s = sc["scalars"]
+    xm, zm, _, _ = O.observation_mesh(x, z, s["slope"], s["sigma_z"], s["mean_z"], 3, 3, 4, 5)
+    seen = []
+    for f in (0.98, 1.02):
+        scal = dict(base, sigma_x=sx_edge * f)
+        res = {}
+        for skip in ("auto", "on", "off"):
+            wp = ops.wake_params(nx=40, nz=40, skip=skip, **scal)
+            res[skip] = (ops.wake_uses_skipping(hist, wp),) + tuple(t.clone() for t in ops.wake_mesh(hist, dlat, wp, _up(xm, dev), _up(zm, dev)))
+        assert res["on"][0] and not res["off"][0]
+        seen.append(res["auto"][0])
+        for k in (1, 2):
+            assert torch.equal(res["auto"][k], res["on"][k]) and torch.equal(res["auto"][k], res["off"][k])
+        assert float(res["auto"][1].abs().max()) > 0
+    assert seen == [True, False]          # smaller bunch -> sparse grid -> skipping; larger bunch -> not
+
+
+def test_fused_exchange_kernel_on_one_gpu(dev):
+    """dfcsr_wake_grid_peers (K4 with the all-gather fused in) with the 'peers' being three grids of THIS GPU: three
+    launches, one per block of the reference's split rule, must leave in every grid exactly the bits of the serial
+    launch.  Covers the N > 1 kernel path on a single-GPU box (the cross-process mapping itself is covered by
+    tests/nccl_worker.py and by the parity record of every multi-GPU bench line)."""
+    import ctypes as C
+    import torch
+    from pydfcsr_b200 import ops
+    from pydfcsr_b200._lib import Axis
+    from pydfcsr_b200.distributed import split_counts
+    sc = scenario.chicane_entry(tilt=0.0)
+    hist, dlat, wp, _ = _device_problem(sc, dev, 40, 40)
+    s = sc["scalars"]
+    x, z = sc["coords"][0], sc["coords"][4]
+    _, _, xr, zr = O.observation_mesh(x, z, s["slope"], s["sigma_z"], s["mean_z"], 3, 3, 5, 7)
+    xa, za = Axis.make(xr[0], xr[-1], 5), Axis.make(zr[0], zr[-1], 7)
+    slope, icpt = float(s["slope"][0]), float(s["slope"][1])
+    de, kick = ops.wake_grid(hist, dlat, wp, xa, za, slope, icpt)
+    n, world = 35, 3
+    grids = [torch.full((2, n), float("nan"), dtype=torch.float64, device=dev) for _ in range(world)]
+    ptrs = (C.c_uint64 * world)(*[g.data_ptr() for g in grids])
+    count, displ = split_counts(n, world)
+    for r in range(world):
+        ops.wake_grid_peers(hist, dlat, wp, xa, za, slope, icpt, first=displ[r], count=count[r], peer_ptrs=ptrs)
+    for g in grids:
+        assert torch.equal(g[0], de) and torch.equal(g[1], kick)
 
 
 def test_fused_sqrt_is_bitwise_the_library_sqrt(dev):
@@ -382,14 +437,13 @@ def test_fused_sqrt_is_bitwise_the_library_sqrt(dev):
 
 @pytest.mark.parametrize("tilt", [0.0, 2.5, -2.5])
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
-def test_zero_density_skipping_is_exact(dev, monkeypatch, tilt, precision):
+def test_zero_density_skipping_is_exact(dev, tilt, precision):
     """dfcsr_history.d_row_support: samples whose eight voxels carry no density and no density gradient add exactly
     0 (every integrand term has a factor rho' or grad rho', CSR.py:732-775), so K4 skips them without loading the
     history.  The result must be BITWISE the one computed without the support table, and on a tilted beam most of
     the in-grid samples must actually be skipped."""
     import torch
     from pydfcsr_b200 import ops
-    monkeypatch.setenv("DFCSR_WAKE_CFG", "46")      # skipping on for every slope (the default enables it for |slope| > 1)
     sc = scenario.chicane_entry(tilt=tilt)
     st, lat = sc["stack"], sc["lattice"]
     nx = nz = 50
@@ -398,7 +452,7 @@ def test_zero_density_skipping_is_exact(dev, monkeypatch, tilt, precision):
     h_off = ops.DeviceHistory.from_stacks(*args, cap=st.shape[0] + 3, head=2, precision=precision, row_support=False)
     assert h_on.support is not None and h_off.support is None
     dlat = ops.DeviceLattice.upload(lat.coords, lat.n_vec, lat.tau_vec, lat.rho, lat.distance, lat.min_s, lat.delta_s, dev)
-    wp = ops.wake_params(nx=nx, nz=nz, **sc["wake_scalars"])
+    wp = ops.wake_params(nx=nx, nz=nz, skip="on", **sc["wake_scalars"])   # on for every slope (AUTO: only sparse grids)
     x, z = sc["coords"][0], sc["coords"][4]
     s = sc["scalars"]
     xm, zm, _, _ = O.observation_mesh(x, z, s["slope"], s["sigma_z"], s["mean_z"], 3, 3, 5, 7)
@@ -425,16 +479,15 @@ def test_zero_density_skipping_is_exact(dev, monkeypatch, tilt, precision):
         assert np.array_equal(sup[(head + k) % cap, :, 0], lo) and np.array_equal(sup[(head + k) % cap, :, 1], hi)
 
 
-def test_zero_density_skipping_empty_and_full_rows(dev, monkeypatch):
+def test_zero_density_skipping_empty_and_full_rows(dev):
     """Degenerate supports: an all-zero history gives exactly zero wakes without gathering anything; a history
     without a single zero voxel skips nothing."""
     import torch
     from pydfcsr_b200 import ops
-    monkeypatch.setenv("DFCSR_WAKE_CFG", "46")
     sc = scenario.chicane_entry(tilt=0.0)
     st, lat = sc["stack"], sc["lattice"]
     dlat = ops.DeviceLattice.upload(lat.coords, lat.n_vec, lat.tau_vec, lat.rho, lat.distance, lat.min_s, lat.delta_s, dev)
-    wp = ops.wake_params(nx=20, nz=33, **sc["wake_scalars"])
+    wp = ops.wake_params(nx=20, nz=33, skip="on", **sc["wake_scalars"])
     x, z = sc["coords"][0], sc["coords"][4]
     s = sc["scalars"]
     xm, zm, _, _ = O.observation_mesh(x, z, s["slope"], s["sigma_z"], s["mean_z"], 3, 3, 3, 4)

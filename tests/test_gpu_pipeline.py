@@ -158,19 +158,15 @@ def test_run_is_bit_reproducible():
         assert torch.equal(u, v)
 
 
-def test_zero_density_skipping_is_bitwise_through_the_whole_chicane(monkeypatch):
+def test_zero_density_skipping_is_bitwise_through_the_whole_chicane():
     """All 133 steps of the chicane (both quadrature branches, |slope| up to ~100, rebuilds, reversed rectangles early
     on) with the wake applied at every evaluation: the run with zero-density skipping (row hulls + coarse s' bracket,
-    DESIGN.md section 4 (vi)) and the run without it (DFCSR_WAKE_CFG=45) must end with the SAME BITS in the last wake
+    DESIGN.md section 4 (vi)) and the run without it (skip_mode OFF) must end with the SAME BITS in the last wake
     grids and in every particle coordinate -- any sample dropped by mistake would have kicked the beam differently."""
     import torch
     from pydfcsr_b200 import CSR2D, synth
 
-    def run(cfg):
-        if cfg is None:
-            monkeypatch.delenv("DFCSR_WAKE_CFG", raising=False)
-        else:
-            monkeypatch.setenv("DFCSR_WAKE_CFG", cfg)
+    def run(skip):
         inp = {"input_beam": {"style": "synthetic", "n_particle": 200_000, "seed": 7},
                "input_lattice": {"lattice_config": synth.chicane_lattice_config()},
                "particle_deposition": dict(xbins=120, zbins=120, xlim=5, zlim=5, filter_order=1, filter_window=9,
@@ -180,10 +176,11 @@ def test_zero_density_skipping_is_bitwise_through_the_whole_chicane(monkeypatch)
                                        write_beam=None, write_wakes=False, workdir="/tmp/dfcsr_test")}
         csr = CSR2D(inp, parallel=False, device="cuda:0", verbose=False)
         csr.wake_counters = torch.zeros(3, dtype=torch.int64, device="cuda:0")
+        csr.skip_mode = skip
         csr.run()
         return csr.dE_dct.clone(), csr.x_kick.clone(), torch.stack(csr.beam.coords), [int(v) for v in csr.wake_counters.cpu()]
 
-    on, off = run(None), run("45")
+    on, off = run("auto"), run("off")
     assert float(on[0].abs().max()) > 0
     for u, v in zip(on[:3], off[:3]):
         assert torch.equal(u, v)
