@@ -1,7 +1,9 @@
-"""Developer tool: time every K4 kernel variant (DFCSR_WAKE_CFG, read per launch by the library) on the bench
-workload in ONE process and compare each variant's wake grids with the round-1 kernel (cfg 1).
+"""Developer tool: time K4 kernel variants (DFCSR_WAKE_CFG, read per launch by the DEVELOPER build of the library,
+tools/build_dev.py) on the bench workload in ONE process and compare each variant's wake grids with the first one.
 
-    python tools/k4_variants.py [reps] [cfg ...]        DFCSR_TILT=2.5 adds an x-z tilt (chirp-band quadrature)
+    python tools/build_dev.py && DFCSR_LIB=pydfcsr_b200/libdfcsr_b200_dev.so python tools/k4_variants.py [reps] [cfg ...]
+    DFCSR_TILT=2.5 adds an x-z tilt (chirp-band quadrature); cfg 0 = shipped default, 50 = direct-gather kernel,
+    60 = patch kernel with the patch disabled, 61.. = patch of 8, 16, ... nodes per warp
 """
 import os
 import sys
@@ -15,7 +17,7 @@ import bench  # noqa: E402
 from pydfcsr_b200 import CSR2D  # noqa: E402
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-cfgs = [int(a) for a in sys.argv[2:]] or [1, 10, 20, 25, 30, 40, 45, 46, 0]
+cfgs = [int(a) for a in sys.argv[2:]] or [50, 0, 60, 64, 68, 72, 78]
 wl = bench.WORKLOAD
 inp = bench._input_dict(wl)
 tilt = os.environ.get("DFCSR_TILT")
