@@ -41,6 +41,7 @@ extern "C" {
 #define DFCSR_STATS_DOUBLES 16
 #define DFCSR_DF_SCALARS 8
 #define DFCSR_MAX_ELEMENTS 256
+#define DFCSR_STAT_BLOCKS 1024      /* chunks of the particle index space in the N-independent reductions */
 #define DFCSR_MAX_PEERS 8          /* ranks of one NVLink/NVSwitch box (dfcsr_wake_grid_peers) */
 
 typedef enum dfcsr_status {
@@ -67,7 +68,8 @@ typedef enum dfcsr_stat {
     DFCSR_S_SLOPE = 4, DFCSR_S_INTERCEPT = 5,      /* polyfit(z, x, 1)            */
     DFCSR_S_MEAN_XT = 6, DFCSR_S_SIGMA_XT = 7,     /* x - polyval(slope, z)       */
     DFCSR_S_SLICE_SIGMA_X = 8, DFCSR_S_SLICE_COUNT = 9, /* |z| < 0.1 sigma_z slice */
-    DFCSR_S_MEAN_PZ = 10, DFCSR_S_SIGMA_PZ = 11, DFCSR_S_N = 12
+    DFCSR_S_MEAN_PZ = 10, DFCSR_S_SIGMA_PZ = 11, DFCSR_S_N = 12,
+    DFCSR_S_ABSMAX_PX = 13                         /* max |px| (for dfcsr_deposit_cic_q); -1 when px was not passed */
 } dfcsr_stat;
 
 /* uniform grid described the way numpy.linspace builds it: node i = i*step + start, last = stop */
@@ -130,12 +132,28 @@ const char* dfcsr_last_error(void);
 int64_t dfcsr_launch_count(void);
 
 /* ---- A14 beam scalars (beams.py:88-98,137-156,201-215; deposit.py:147-159) --------------------
- * Two reduction passes over (x, z[, pz]); results land in d_stats[DFCSR_STATS_DOUBLES].
- * d_workspace needs dfcsr_beam_stats_workspace() bytes, ZERO-INITIALISED once by the caller (the
- * calls leave it reusable).  d_pz may be NULL. */
+ * Two reduction passes over (x, z[, pz][, px]); results land in d_stats[DFCSR_STATS_DOUBLES].
+ * The reductions do not depend on how the particles are distributed: the index space [0, n) is cut into
+ * DFCSR_STAT_BLOCKS contiguous chunks of dfcsr_stat_chunk(n) particles, one CTA reduces one chunk in a fixed order and a
+ * (1024, 8) table of chunk totals is summed in a fixed order.  A run that shards the particles over N GPUs in whole
+ * chunks (dfcsr_beam_stats_partial on every rank, rows stored into the tables of all ranks over NVLink peer memory, a
+ * barrier, dfcsr_beam_stats_final) therefore returns the SAME BITS as dfcsr_beam_stats on one GPU.
+ * h_centre: 3 HOST doubles (x, z, pz) about which pass A accumulates, e.g. the previous means (NULL = zeros); it
+ * must be the same on every rank.  d_workspace needs dfcsr_beam_stats_workspace() bytes, ZERO-INITIALISED once by the
+ * caller (the calls leave it reusable).  d_pz and d_px may be NULL. */
 int64_t dfcsr_beam_stats_workspace(void);
-int dfcsr_beam_stats(const double* d_x, const double* d_z, const double* d_pz, int64_t n,
-                     double* d_stats, void* d_workspace, void* stream);
+int64_t dfcsr_stat_chunk(int64_t n_total);     /* particles per chunk: ceil(n_total / DFCSR_STAT_BLOCKS) */
+int dfcsr_beam_stats(const double* d_x, const double* d_z, const double* d_pz, const double* d_px, int64_t n,
+                     const double* h_centre, double* d_stats, void* d_workspace, void* stream);
+/* pass 0 (moments) or 1 (residuals; reads pass 0's results from d_stats) over this rank's shard: chunks
+ * [first_block, first_block + n_blocks) = n_local particles.  Rows go to d_table ((1024, 8) doubles) and to the tables
+ * of the n_peers ranks listed in h_peer_tables (HOST array of addresses valid in this process; may include d_table). */
+int dfcsr_beam_stats_partial(int32_t pass, const double* d_x, const double* d_z, const double* d_pz, const double* d_px,
+                             int64_t n_local, int64_t n_total, int32_t first_block, int32_t n_blocks,
+                             const double* h_centre, double* d_stats, double* d_table,
+                             const uint64_t* h_peer_tables, int32_t n_peers, void* stream);
+int dfcsr_beam_stats_final(int32_t pass, const double* d_table, int64_t n_total, const double* h_centre,
+                           int32_t have_pz, int32_t have_px, double* d_stats, void* stream);
 
 /* n doubles from device memory into PINNED host memory (cudaHostAlloc / cudaHostRegister, mapped), stored by a one-warp
  * kernel instead of the device-to-host copy engine, so that a small result the host is waiting for (the 16 statistics
@@ -144,21 +162,29 @@ int dfcsr_beam_stats(const double* d_x, const double* d_z, const double* d_pz, i
 int dfcsr_mirror_to_host(const double* d_src, double* h_dst, int32_t n, void* stream);
 
 /* ---- 6 x 6 phase-space covariance (twiss.py:2-71: np.cov([x, px, pz]) and np.cov([y, py, pz]) per step,
- * CSR.py:837-859) -- one read of the six coordinate arrays, deterministic reduction.
+ * CSR.py:837-859) -- one read of the six coordinate arrays, same chunked, distribution-independent reduction.
  * d_out[27]: means of (x, px, y, py, z, pz), then the upper triangle (i <= j, row-major) of the covariance
- * with np.cov's 1/(n-1) normalisation.  d_workspace: dfcsr_beam_cov_workspace() bytes, zero-initialised once. */
+ * with np.cov's 1/(n-1) normalisation.  h_centre: 6 HOST doubles (NULL = zeros).  d_workspace:
+ * dfcsr_beam_cov_workspace() bytes, zero-initialised once.  _partial / _final: as for the statistics, table (1024, 27). */
 int64_t dfcsr_beam_cov_workspace(void);
 int dfcsr_beam_cov(const double* d_x, const double* d_px, const double* d_y, const double* d_py,
-                   const double* d_z, const double* d_pz, int64_t n, double* d_out, void* d_workspace,
-                   void* stream);
+                   const double* d_z, const double* d_pz, int64_t n, const double* h_centre, double* d_out,
+                   void* d_workspace, void* stream);
+int dfcsr_beam_cov_partial(const double* d_x, const double* d_px, const double* d_y, const double* d_py,
+                           const double* d_z, const double* d_pz, int64_t n_local, int64_t n_total,
+                           int32_t first_block, int32_t n_blocks, const double* h_centre, double* d_table,
+                           const uint64_t* h_peer_tables, int32_t n_peers, void* stream);
+int dfcsr_beam_cov_final(const double* d_table, int64_t n_total, const double* h_centre, double* d_out, void* stream);
 
 /* ---- A1 / K1 particle deposition (deposit.py:42-87, called at deposit.py:172,178) --------------
  * One pass deposits both weights (w = 1 and w = px) with CIC on an (nx, nz) grid whose bin spacing
  * is (end - start) / n.  d_count / d_vxsum (nx*nz doubles each) are zeroed by the call.
  * mode 0 = automatic (4 for n >= 65536, else 5);
- * 4 = 64-bit fixed-point block-private shared-memory tile, 5 = 64-bit fixed-point L2 reductions: integer
- *     accumulation, bit-reproducible from run to run and across ranks, cell sums within ~1e-14 of the largest
- *     cell (a non-finite px makes d_vxsum NaN everywhere and leaves d_count unaffected);
+ * 4 = 64-bit fixed-point block-private shared-memory tile, 5 = 64-bit fixed-point L2 reductions: every particle's
+ *     contribution is rounded ONCE to a 2^-f grid that depends on n only, everything after is integer addition:
+ *     bit-reproducible from run to run, independent of the launch geometry and of how the particles are split over
+ *     GPUs; cell sums within ~1e-13 of the largest cell (a non-finite px makes d_vxsum NaN everywhere and leaves
+ *     d_count unaffected);
  * 1 = fp64 tile + warp match, 2 = fp64 L2 reductions, 3 = fp64 tile (summation order, hence the last bits,
  *     vary from run to run). */
 int dfcsr_deposit_cic(const double* d_x, const double* d_z, const double* d_px, int64_t n,
@@ -168,6 +194,21 @@ int dfcsr_deposit_cic(const double* d_x, const double* d_z, const double* d_px, 
 
 /* NGP counts (no reference counterpart): i = floor((q - start)/spacing + 0.5),
  * +1 iff both indices are in range; int64 counts, bit-exact for any summation order. */
+/* The fixed-point deposit in two stages, for particles sharded over ranks (CSR.py replicates the particles on every
+ * MPI rank; here K1 may take 1/N of them per GPU):
+ * _q      deposits this rank's n_local particles into d_q, a (2, nx*nz) int64 buffer [count | vxsum] (zeroed by the
+ *         call) at the fixed-point scales of the WHOLE bunch (n_total particles, absmax_px = max |px| over all of
+ *         them = stats[DFCSR_S_ABSMAX_PX] of the statistics pass);
+ * _finish adds the buffers of all ranks -- h_peer_q: n_peers HOST entries, addresses valid in this process (NVLink peer
+ *         mappings; a single rank passes its own buffer) -- and converts to the fp64 grids of dfcsr_deposit_cic.
+ * Integer addition is exact: every rank gets the bits of dfcsr_deposit_cic (mode 4/5) over all particles on one GPU.
+ * The caller puts a cross-rank barrier between the two stages and before the buffers are written again. */
+int dfcsr_deposit_cic_q(const double* d_x, const double* d_z, const double* d_px, int64_t n_local, int64_t n_total,
+                        int32_t nx, double x_start, double x_end, int32_t nz, double z_start, double z_end,
+                        double absmax_px, int64_t* d_q, void* stream);
+int dfcsr_deposit_cic_finish(const uint64_t* h_peer_q, int32_t n_peers, int32_t nx, int32_t nz, int64_t n_total,
+                             double absmax_px, double* d_count, double* d_vxsum, void* stream);
+
 int dfcsr_deposit_ngp(const double* d_x, const double* d_z, int64_t n,
                       int32_t nx, double x_start, double x_end,
                       int32_t nz, double z_start, double z_end,

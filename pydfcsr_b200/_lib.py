@@ -23,7 +23,8 @@ SKIP_MODES = {"auto": 0, "on": 1, "off": 2}
 
 # indices of dfcsr_stat
 (S_MEAN_X, S_MEAN_Z, S_SIGMA_X, S_SIGMA_Z, S_SLOPE, S_INTERCEPT, S_MEAN_XT, S_SIGMA_XT,
- S_SLICE_SIGMA_X, S_SLICE_COUNT, S_MEAN_PZ, S_SIGMA_PZ, S_N) = range(13)
+ S_SLICE_SIGMA_X, S_SLICE_COUNT, S_MEAN_PZ, S_SIGMA_PZ, S_N, S_ABSMAX_PX) = range(14)
+STAT_BLOCKS = 1024
 
 
 class Axis(C.Structure):
@@ -64,11 +65,20 @@ SIGNATURES = {
     "dfcsr_last_error": (C.c_char_p, []),
     "dfcsr_launch_count": (_L, []),
     "dfcsr_beam_stats_workspace": (_L, []),
-    "dfcsr_beam_stats": (C.c_int, [_P, _P, _P, _L, _P, _P, _P]),
+    "dfcsr_stat_chunk": (_L, [_L]),
+    "dfcsr_beam_stats": (C.c_int, [_P, _P, _P, _P, _L, C.POINTER(C.c_double), _P, _P, _P]),
+    "dfcsr_beam_stats_partial": (C.c_int, [_I, _P, _P, _P, _P, _L, _L, _I, _I, C.POINTER(C.c_double), _P, _P,
+                                           C.POINTER(C.c_uint64), _I, _P]),
+    "dfcsr_beam_stats_final": (C.c_int, [_I, _P, _L, C.POINTER(C.c_double), _I, _I, _P, _P]),
     "dfcsr_mirror_to_host": (C.c_int, [_P, _P, _I, _P]),
     "dfcsr_beam_cov_workspace": (_L, []),
-    "dfcsr_beam_cov": (C.c_int, [_P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
+    "dfcsr_beam_cov": (C.c_int, [_P, _P, _P, _P, _P, _P, _L, C.POINTER(C.c_double), _P, _P, _P]),
+    "dfcsr_beam_cov_partial": (C.c_int, [_P, _P, _P, _P, _P, _P, _L, _L, _I, _I, C.POINTER(C.c_double), _P,
+                                         C.POINTER(C.c_uint64), _I, _P]),
+    "dfcsr_beam_cov_final": (C.c_int, [_P, _L, C.POINTER(C.c_double), _P, _P]),
     "dfcsr_deposit_cic": (C.c_int, [_P, _P, _P, _L, _I, _D, _D, _I, _D, _D, _P, _P, _I, _P]),
+    "dfcsr_deposit_cic_q": (C.c_int, [_P, _P, _P, _L, _L, _I, _D, _D, _I, _D, _D, _D, _P, _P]),
+    "dfcsr_deposit_cic_finish": (C.c_int, [C.POINTER(C.c_uint64), _I, _I, _I, _L, _D, _P, _P, _P]),
     "dfcsr_deposit_ngp": (C.c_int, [_P, _P, _L, _I, _D, _D, _I, _D, _D, _P, _P]),
     "dfcsr_make_df_workspace": (_L, [_I, _I]),
     "dfcsr_make_df": (C.c_int, [_P, _P, Axis, Axis, _I, _P, _P, _P, _D, _P, _P, _P, _P]),

@@ -18,7 +18,10 @@ MC2 = 0.51099895e6      # electron rest energy [eV] (physical_constants.py)
 
 
 class Beam:
-    def __init__(self, input_beam, device=None):
+    def __init__(self, input_beam, device=None, shards=None):
+        """shards: None (all particles on this GPU, like every MPI rank of the reference), or a callable
+        n_total -> distributed.ParticleShards: this rank then keeps only its chunks of the bunch, and the statistics,
+        the covariance and (through DF_tracker) the deposit combine the shards exactly (bit-identical to one GPU)."""
         self.check_inputs(input_beam)
         self.input_beam_config = input_beam
         self.style = input_beam["style"]
@@ -55,6 +58,13 @@ class Beam:
                                -299792458.0 * pg.beta * (pg.t - np.mean(pg.t)), (pg.p - p0c) / p0c])
         else:
             raise ImportError("input_beam style 'ParticleGroup' needs pmd_beamphysics/h5py (not available offline)")
+        self.n_total = int(coords.shape[1])
+        # centre of the first statistics pass: the first particle of the WHOLE bunch (known on every rank before sharding)
+        self._centre = [float(coords[0][0]), float(coords[4][0]), float(coords[5][0])]
+        self._centre6 = [float(coords[k][0]) for k in range(6)]
+        self.shards = shards(self.n_total) if callable(shards) else shards
+        if self.shards is not None:
+            coords = self.shards.local_slice(coords)
         if isinstance(coords, torch.Tensor):
             c = coords.to(self.device, torch.float64)
         else:
@@ -87,12 +97,16 @@ class Beam:
         """One pass of the device reductions replaces np.std/np.mean/np.polyfit (beams.py:88-98).  The pass is only
         ENQUEUED here; the host waits for it when a statistic is first read (`stats`, `_sigma_x`, `_slope`, ...), so the
         caller can keep launching work -- the reduction that follows a kick overlaps with whatever is enqueued next."""
-        self._pending_stats = ops.beam_stats_async(self.x, self.z, self.pz)
+        self._pending_stats = ops.beam_stats_async(self.x, self.z, self.pz, self.px, centre=self._centre, shards=self.shards)
 
     @property
     def stats(self):
-        """The 16 doubles of `dfcsr_beam_stats` for the current particle state (blocks until they have arrived)."""
-        return self._pending_stats.get()
+        """The 16 doubles of `dfcsr_beam_stats` for the current particle state (blocks until they have arrived).
+        Reading them also moves the centre of the next first pass to the current means -- a deterministic rule (it follows
+        the program order, not the timing), identical on every rank and for every way of sharding the particles."""
+        st = self._pending_stats.get()
+        self._centre = [float(st[_lib.S_MEAN_X]), float(st[_lib.S_MEAN_Z]), float(st[_lib.S_MEAN_PZ])]
+        return st
 
     _sigma_x = property(lambda self: float(self.stats[_lib.S_SIGMA_X]))
     _sigma_z = property(lambda self: float(self.stats[_lib.S_SIGMA_Z]))
@@ -135,7 +149,7 @@ class Beam:
     init_energy = property(lambda self: self._init_energy)
     init_gamma = property(lambda self: self._init_gamma)
     charge = property(lambda self: self._charge)
-    mean_y = property(lambda self: float(self.y.mean()))
+    mean_y = property(lambda self: float(ops.beam_cov(self.coords, centre=self._centre6, shards=self.shards)[0][2]))
     mean_energy = property(lambda self: (float(self.stats[_lib.S_MEAN_PZ]) + 1) * self._init_energy)
     sigma_energy = property(lambda self: float(self.stats[_lib.S_SIGMA_PZ]) * self._init_energy)
     sigma_x_transform = property(lambda self: float(self.stats[_lib.S_SIGMA_XT]))
@@ -158,7 +172,7 @@ class Beam:
     def twiss(self):
         """Twiss/dispersion from the 3x3 covariances of (x, px, pz) and (y, py, pz) (twiss.py:2-71); the 6x6
         covariance comes from one device reduction (ops.beam_cov)."""
-        _, cov6 = ops.beam_cov(self.coords)
+        _, cov6 = ops.beam_cov(self.coords, centre=self._centre6, shards=self.shards)
         out = {}
         for plane, idx in (("x", (0, 1, 5)), ("y", (2, 3, 5))):
             cov = cov6[np.ix_(idx, idx)]
@@ -171,4 +185,7 @@ class Beam:
         return out
 
     def to_host(self) -> np.ndarray:
+        """(6, n_total) host array of ALL particles (collective when the particles are sharded)."""
+        if self.shards is not None:
+            return torch.stack([self.shards.gather(c) for c in self.coords]).cpu().numpy()
         return torch.stack(self.coords).cpu().numpy()

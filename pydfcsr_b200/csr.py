@@ -39,10 +39,16 @@ def isotime():
 
 
 class CSR2D:
-    def __init__(self, input_file=None, parallel=False, device=None, verbose=True, precision="fp64"):
+    def __init__(self, input_file=None, parallel=False, device=None, verbose=True, precision="fp64", shard_particles=None):
         """precision='fp32' selects the optional mixed-precision history (wakes within 1e-4; default is
-        the fp64 parity mode).  Everything else is the reference's signature."""
+        the fp64 parity mode).  shard_particles (parallel runs): True = every rank tracks, deposits and kicks 1/N of
+        the particles and the shards are combined exactly (statistics tables, integer deposit grids) -- same bits as
+        replicating them; False = every rank keeps all particles like every MPI rank of the reference; None = True
+        unless DFCSR_SHARD_PARTICLES=0.  Everything else is the reference's signature."""
         self.precision = precision
+        if shard_particles is None:
+            shard_particles = os.environ.get("DFCSR_SHARD_PARTICLES", "1") != "0"
+        self.shard_particles = bool(shard_particles) and bool(parallel)
         self.timestamp = isotime()
         self.verbose = verbose
         self.parallel = bool(parallel)
@@ -68,9 +74,15 @@ class CSR2D:
         inp = parse_yaml(input_file)
         self.check_input_consistency(inp)
         self.input = inp
-        self.beam = Beam(inp["input_beam"], device=self.device)
+        shards = None
+        if self.shard_particles and self.world_size > 1:
+            dep = inp.get("particle_deposition") or {}
+            cells = max(100 * 100, int(dep.get("xbins", 100)) * int(dep.get("zbins", 100)))     # deposit.py:160-167
+            shards = lambda n: dist_utils.ParticleShards(n, self.device, cells)                  # noqa: E731
+        self.beam = Beam(inp["input_beam"], device=self.device, shards=shards)
         self.lattice = Lattice(inp["input_lattice"])
-        self.DF_tracker = DF_tracker(inp.get("particle_deposition"), device=self.device, precision=self.precision)
+        self.DF_tracker = DF_tracker(inp.get("particle_deposition"), device=self.device, precision=self.precision,
+                                     shards=self.beam.shards)
         self.integration_params = Integration_params(inp.get("CSR_integration"))
         self.CSR_params = CSR_params(inp.get("CSR_computation"))
 
@@ -347,12 +359,15 @@ class CSR2D:
     # The reference writes HDF5 (CSR.py:784-879); h5py is not available offline, so the same
     # content goes to .npz files with the same group/dataset names flattened into keys.
     def dump_beam(self, label):
-        if self.rank != 0 or not getattr(self.CSR_params, "write_beam", None):
+        if not getattr(self.CSR_params, "write_beam", None):
+            return
+        coords = self.beam.to_host() if (self.beam.shards is not None or self.rank == 0) else None   # collective if sharded
+        if self.rank != 0:
             return
         path = full_path(self.CSR_params.workdir)
         os.makedirs(path, exist_ok=True)
         fn = os.path.join(path, f"{self.prefix}-particles-{label}.npz")
-        np.savez(fn, coords=self.beam.to_host(), position=self.beam.position, charge=self.beam.charge,
+        np.savez(fn, coords=coords, position=self.beam.position, charge=self.beam.charge,
                  energy=self.beam.init_energy)
         self._log("Beam at position {} is written to {}".format(self.beam.position, fn))
 

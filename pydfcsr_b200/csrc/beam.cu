@@ -9,121 +9,200 @@
 // dfcsr_apply_kick replaces Beam.apply_wakes (beams.py:108-131): bilinear samples
 // (RegularGridInterpolator, fill 0) of the two wake grids at (x - polyval(slope, z), z).
 // Bound: HBM, 48 B / particle (read x, z, px, pz; write px, pz).
+#include <math_constants.h>
 #include "common.cuh"
 
 namespace dfcsr {
 
+// ---- reductions that do not depend on how the particles are distributed over GPUs ------------------------------
+// The particle index space [0, n_total) is cut into DFCSR_STAT_BLOCKS contiguous chunks of C = ceil(n_total / 1024)
+// particles.  One CTA reduces one chunk in a fixed order (thread t takes particles t, t + 256, ... of the chunk, then
+// a fixed warp butterfly, then the warps in order) and publishes one row of a (1024, NV) table; the table is summed
+// in a fixed order by one CTA.  Which GPU reduced which chunk is irrelevant: a run on N GPUs, each holding whole
+// chunks, produces the same bits as a run on one.  With several ranks the rows are stored straight into the tables of
+// all ranks (NVLink peer memory) and a barrier + dfcsr_*_final follow; a single rank lets the last CTA do the final sum.
 constexpr int kStatThreads = 256;
-constexpr int kStatBlocks = 148 * 4;
+constexpr int kStatBlocks = DFCSR_STAT_BLOCKS;
 constexpr int kStatVals = 8;
+constexpr int kCovVals = 27;
 
 struct StatWorkspace {
     double partial[2][kStatBlocks][kStatVals];
     unsigned int ticket[4];   // must be zero before the first call; every pass leaves its ticket at zero
 };
 
-template <int NV, int kStride = kStatVals>
-__device__ __forceinline__ bool block_reduce_publish(double (&v)[NV], double (*partial)[kStride],
-                                                     unsigned int* ticket, double (&total)[NV]) {
+struct CovWorkspace {
+    double partial[kStatBlocks][kCovVals];
+    unsigned int ticket[4];
+};
+
+struct PeerTables {
+    double* tab[DFCSR_MAX_PEERS];
+    int n;
+};
+
+__device__ __forceinline__ double absmax_merge(double m, double a) {      // NaN is sticky (fmax would drop it)
+    return (a != a || m != m) ? CUDART_NAN : fmax(m, a);
+}
+
+// block totals of v[0..NV) in thread 0; entry kMaxIdx (if >= 0) is a maximum, all others are sums
+template <int NV, int kMaxIdx>
+__device__ __forceinline__ void block_total(double (&v)[NV]) {
     __shared__ double sm[kStatThreads / 32][NV];
-    __shared__ bool last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+    for (int k = 0; k < NV; ++k) {
+        if (k == kMaxIdx) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[k] = absmax_merge(v[k], __shfl_xor_sync(0xffffffffu, v[k], o));
+        } else {
+            v[k] = warp_sum(v[k]);
+        }
+    }
+    __syncthreads();                       // sm may still be read by a previous call
     if (lane == 0)
         for (int k = 0; k < NV; ++k) sm[warp][k] = v[k];
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int k = 0; k < NV; ++k) {
-            double s = 0.0;
-            for (int w = 0; w < kStatThreads / 32; ++w) s += sm[w][k];
-            partial[blockIdx.x][k] = s;
+            double s = sm[0][k];
+            for (int w = 1; w < kStatThreads / 32; ++w) s = (k == kMaxIdx) ? absmax_merge(s, sm[w][k]) : s + sm[w][k];
+            v[k] = s;
         }
+    }
+}
+
+// fixed-order total of a (kStatBlocks, NV) table; result in thread 0 (called by all 256 threads of ONE block)
+template <int NV, int kMaxIdx>
+__device__ __forceinline__ void table_total(const double* table, double (&tot)[NV]) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double s = (k == kMaxIdx) ? 0.0 : 0.0;
+        for (int b = threadIdx.x; b < kStatBlocks; b += kStatThreads) {
+            const double p = ((const volatile double*)table)[(size_t)b * NV + k];
+            s = (k == kMaxIdx) ? absmax_merge(s, p) : s + p;
+        }
+        tot[k] = s;
+    }
+    block_total<NV, kMaxIdx>(tot);
+}
+
+// publish one table row: local table and, with several ranks, every peer's table
+template <int NV>
+__device__ __forceinline__ void publish_row(const double (&v)[NV], int row, double* table, const PeerTables& peers) {
+    for (int k = 0; k < NV; ++k) table[(size_t)row * NV + k] = v[k];
+#pragma unroll
+    for (int p = 0; p < DFCSR_MAX_PEERS; ++p)
+        if (p < peers.n && peers.tab[p] != table)
+            for (int k = 0; k < NV; ++k) peers.tab[p][(size_t)row * NV + k] = v[k];
+}
+
+// single-rank mode: the last CTA to publish its row does the final sum.  true in thread 0 of that CTA, with tot filled.
+template <int NV, int kMaxIdx>
+__device__ __forceinline__ bool last_block_total(unsigned int* ticket, const double* table, double (&tot)[NV]) {
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
         __threadfence();
-        unsigned int t = atomicAdd(ticket, 1u);
+        const unsigned int t = atomicAdd(ticket, 1u);
         last = (t == gridDim.x - 1);
     }
     __syncthreads();
     if (!last) return false;
     __threadfence();
-    // the last block to arrive sums the partials in block order (deterministic)
-    for (int k = 0; k < NV; ++k) {
-        double s = 0.0;
-        for (int b = threadIdx.x; b < (int)gridDim.x; b += kStatThreads) s += ((volatile double*)&partial[b][k])[0];
-        v[k] = s;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
-    if (lane == 0)
-        for (int k = 0; k < NV; ++k) sm[warp][k] = v[k];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int k = 0; k < NV; ++k) {
-            double s = 0.0;
-            for (int w = 0; w < kStatThreads / 32; ++w) s += sm[w][k];
-            total[k] = s;
-        }
-        *ticket = 0u;
-    }
+    table_total<NV, kMaxIdx>(table, tot);
+    if (threadIdx.x == 0) *ticket = 0u;
     return threadIdx.x == 0;
 }
 
-// Pass A: first and second moments in ONE read of (x, z[, pz]).  Sums are taken about the first particle
-// (x[0], z[0], pz[0]) so that E[d^2] - E[d]^2 loses at most ~1 digit even for a bunch far from the origin.
+struct Centre3 { double x, z, p; };
+
+__device__ __forceinline__ void finish_moments(const double (&tot)[kStatVals], long long n, Centre3 c, bool have_pz,
+                                               bool have_px, double* __restrict__ stats) {
+    const double inv_n = 1.0 / (double)n;
+    const double ex = tot[0] * inv_n, ez = tot[1] * inv_n, ep = tot[5] * inv_n;
+    const double vxx = fmax(tot[2] * inv_n - ex * ex, 0.0);
+    const double vzz = fmax(tot[3] * inv_n - ez * ez, 0.0);
+    const double cxz = tot[4] * inv_n - ex * ez;
+    const double mx = c.x + ex, mz = c.z + ez;
+    stats[DFCSR_S_MEAN_X] = mx;
+    stats[DFCSR_S_MEAN_Z] = mz;
+    stats[DFCSR_S_SIGMA_X] = sqrt(vxx);     // np.std: population (ddof = 0)
+    stats[DFCSR_S_SIGMA_Z] = sqrt(vzz);
+    const double slope = cxz / vzz;           // least-squares line x = slope z + b (np.polyfit(z, x, 1))
+    stats[DFCSR_S_SLOPE] = slope;
+    stats[DFCSR_S_INTERCEPT] = mx - slope * mz;
+    stats[DFCSR_S_MEAN_PZ] = have_pz ? c.p + ep : 0.0;
+    stats[DFCSR_S_SIGMA_PZ] = have_pz ? sqrt(fmax(tot[6] * inv_n - ep * ep, 0.0)) : 0.0;
+    stats[DFCSR_S_N] = (double)n;
+    stats[DFCSR_S_ABSMAX_PX] = have_px ? tot[7] : -1.0;
+}
+
+__device__ __forceinline__ void finish_residuals(const double (&tot)[kStatVals], long long n, double* __restrict__ stats) {
+    const double mx = stats[DFCSR_S_MEAN_X], mz = stats[DFCSR_S_MEAN_Z];
+    double me = tot[0] / (double)n;
+    stats[DFCSR_S_MEAN_XT] = me;
+    stats[DFCSR_S_SIGMA_XT] = sqrt(fmax(tot[1] / (double)n - me * me, 0.0));
+    double c = tot[4];
+    double ms = tot[2] / c;
+    stats[DFCSR_S_SLICE_SIGMA_X] = sqrt(fmax(tot[3] / c - ms * ms, 0.0));
+    stats[DFCSR_S_SLICE_COUNT] = c;
+    stats[DFCSR_S_SIGMA_X] = sqrt(tot[5] / (double)n);
+    stats[DFCSR_S_SIGMA_Z] = sqrt(tot[6] / (double)n);
+    const double slope2 = tot[7] / tot[6];
+    stats[DFCSR_S_SLOPE] = slope2;
+    stats[DFCSR_S_INTERCEPT] = mx - slope2 * mz;
+}
+
+// Pass A: first and second moments in ONE read of (x, z[, pz][, px]).  Sums are taken about a centre the caller supplies
+// (the previous step's means: E[d^2] - E[d]^2 then loses at most ~1 digit even for a bunch far from the origin; pass B
+// recomputes the second moments about the true means anyway).  Entry 7 is max|px| for the fixed-point deposit.
+// Pointers are those of this rank's shard; CTA b reduces chunk first_block + b, i.e. local particles [b C, (b+1) C).
 __global__ void __launch_bounds__(kStatThreads)
 stats_moments(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ pz,
-              long long n, double* __restrict__ stats, StatWorkspace* ws) {
-    const double cx = x[0], cz = z[0], cp = pz ? pz[0] : 0.0;
+              const double* __restrict__ px, long long n_local, long long chunk, long long n_total, int first_block,
+              Centre3 c, double* __restrict__ table, PeerTables peers, unsigned int* ticket, double* __restrict__ stats) {
     double v[kStatVals];
 #pragma unroll
     for (int k = 0; k < kStatVals; ++k) v[k] = 0.0;
-    for (long long i = (long long)blockIdx.x * kStatThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kStatThreads) {
-        double dx = x[i] - cx, dz = z[i] - cz;
+    const long long lo = (long long)blockIdx.x * chunk;
+    const long long hi = (lo + chunk < n_local) ? lo + chunk : n_local;
+    for (long long i = lo + threadIdx.x; i < hi; i += kStatThreads) {
+        double dx = x[i] - c.x, dz = z[i] - c.z;
         v[0] += dx;
         v[1] += dz;
         v[2] = fma(dx, dx, v[2]);
         v[3] = fma(dz, dz, v[3]);
         v[4] = fma(dx, dz, v[4]);
         if (pz) {
-            double dp = pz[i] - cp;
+            double dp = pz[i] - c.p;
             v[5] += dp;
             v[6] = fma(dp, dp, v[6]);
         }
+        if (px) v[7] = absmax_merge(v[7], fabs(px[i]));
     }
-    double tot[kStatVals];
-    if (block_reduce_publish<kStatVals>(v, ws->partial[0], &ws->ticket[0], tot)) {
-        const double inv_n = 1.0 / (double)n;
-        const double ex = tot[0] * inv_n, ez = tot[1] * inv_n, ep = tot[5] * inv_n;
-        const double vxx = fmax(tot[2] * inv_n - ex * ex, 0.0);
-        const double vzz = fmax(tot[3] * inv_n - ez * ez, 0.0);
-        const double cxz = tot[4] * inv_n - ex * ez;
-        const double mx = cx + ex, mz = cz + ez;
-        stats[DFCSR_S_MEAN_X] = mx;
-        stats[DFCSR_S_MEAN_Z] = mz;
-        stats[DFCSR_S_SIGMA_X] = sqrt(vxx);     // np.std: population (ddof = 0)
-        stats[DFCSR_S_SIGMA_Z] = sqrt(vzz);
-        const double slope = cxz / vzz;           // least-squares line x = slope z + b (np.polyfit(z, x, 1))
-        stats[DFCSR_S_SLOPE] = slope;
-        stats[DFCSR_S_INTERCEPT] = mx - slope * mz;
-        stats[DFCSR_S_MEAN_PZ] = cp + ep;
-        stats[DFCSR_S_SIGMA_PZ] = sqrt(fmax(tot[6] * inv_n - ep * ep, 0.0));
-        stats[DFCSR_S_N] = (double)n;
+    block_total<kStatVals, 7>(v);
+    if (threadIdx.x == 0) publish_row<kStatVals>(v, first_block + blockIdx.x, table, peers);
+    if (ticket) {
+        double tot[kStatVals];
+        if (last_block_total<kStatVals, 7>(ticket, table, tot)) finish_moments(tot, n_total, c, pz != nullptr, px != nullptr, stats);
     }
 }
 
 // Pass B: statistics that need pass A's results: x_transform = x - polyval(slope, z) (CSR.py:368-372) and the
 // central slice |z| < 0.1 sigma_z of DF_tracker.get_DF (deposit.py:157-159).
 __global__ void __launch_bounds__(kStatThreads)
-stats_residuals(const double* __restrict__ x, const double* __restrict__ z, long long n,
-                double* __restrict__ stats, StatWorkspace* ws) {
+stats_residuals(const double* __restrict__ x, const double* __restrict__ z, long long n_local, long long chunk,
+                long long n_total, int first_block, double* __restrict__ table, PeerTables peers, unsigned int* ticket,
+                double* __restrict__ stats) {
     const double mx = stats[DFCSR_S_MEAN_X], mz = stats[DFCSR_S_MEAN_Z];
     const double slope = stats[DFCSR_S_SLOPE];
     const double cut = 0.1 * stats[DFCSR_S_SIGMA_Z];
     double v[kStatVals];
 #pragma unroll
     for (int k = 0; k < kStatVals; ++k) v[k] = 0.0;
-    for (long long i = (long long)blockIdx.x * kStatThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kStatThreads) {
+    const long long lo = (long long)blockIdx.x * chunk;
+    const long long hi = (lo + chunk < n_local) ? lo + chunk : n_local;
+    for (long long i = lo + threadIdx.x; i < hi; i += kStatThreads) {
         double zi = z[i];
         double dx = x[i] - mx, dz = zi - mz;
         double e = dx - slope * dz;          // x_transform up to the (rounding-level) constant term
@@ -138,50 +217,58 @@ stats_residuals(const double* __restrict__ x, const double* __restrict__ z, long
             v[4] += 1.0;
         }
     }
+    block_total<kStatVals, -1>(v);
+    if (threadIdx.x == 0) publish_row<kStatVals>(v, first_block + blockIdx.x, table, peers);
+    if (ticket) {
+        double tot[kStatVals];
+        if (last_block_total<kStatVals, -1>(ticket, table, tot)) finish_residuals(tot, n_total, stats);
+    }
+}
+
+// final sums after the cross-rank exchange (one CTA); pass 0 = moments, 1 = residuals
+__global__ void __launch_bounds__(kStatThreads)
+stats_final_kernel(int pass, const double* __restrict__ table, long long n_total, Centre3 c, int have_pz, int have_px,
+                   double* __restrict__ stats) {
     double tot[kStatVals];
-    if (block_reduce_publish<kStatVals>(v, ws->partial[1], &ws->ticket[1], tot)) {
-        double me = tot[0] / (double)n;
-        stats[DFCSR_S_MEAN_XT] = me;
-        stats[DFCSR_S_SIGMA_XT] = sqrt(fmax(tot[1] / (double)n - me * me, 0.0));
-        double c = tot[4];
-        double ms = tot[2] / c;
-        stats[DFCSR_S_SLICE_SIGMA_X] = sqrt(fmax(tot[3] / c - ms * ms, 0.0));
-        stats[DFCSR_S_SLICE_COUNT] = c;
-        stats[DFCSR_S_SIGMA_X] = sqrt(tot[5] / (double)n);
-        stats[DFCSR_S_SIGMA_Z] = sqrt(tot[6] / (double)n);
-        const double slope2 = tot[7] / tot[6];
-        stats[DFCSR_S_SLOPE] = slope2;
-        stats[DFCSR_S_INTERCEPT] = mx - slope2 * mz;
+    if (pass == 0) {
+        table_total<kStatVals, 7>(table, tot);
+        if (threadIdx.x == 0) finish_moments(tot, n_total, c, have_pz != 0, have_px != 0, stats);
+    } else {
+        table_total<kStatVals, -1>(table, tot);
+        if (threadIdx.x == 0) finish_residuals(tot, n_total, stats);
     }
 }
 
 // ---- 6 x 6 covariance of the phase-space coordinates (Twiss / dispersion statistics, twiss.py:2-71) ------
-// One read of the six coordinate arrays: sums and upper-triangle products about the first particle, reduced in
-// fixed order like the passes above.  out[0..5] = means, out[6..26] = covariance (i <= j, row-major over the
-// upper triangle) with np.cov's normalisation 1/(n-1).
-constexpr int kCovVals = 27;
-
-struct CovWorkspace {
-    double partial[kStatBlocks][kCovVals];
-    unsigned int ticket[4];
-};
-
+// One read of the six coordinate arrays: sums and upper-triangle products about a caller-supplied centre, reduced like
+// the passes above.  out[0..5] = means, out[6..26] = covariance (i <= j, row-major over the upper triangle) with
+// np.cov's normalisation 1/(n-1).
 struct SixPtr {
     const double* q[6];
 };
 
+struct Centre6 { double o[6]; };
+
+__device__ __forceinline__ void finish_cov(const double (&tot)[kCovVals], long long n, const Centre6& c, double* __restrict__ out) {
+    const double inv_n = 1.0 / (double)n, inv_n1 = 1.0 / (double)(n - 1);
+    for (int a = 0; a < 6; ++a) out[a] = c.o[a] + tot[a] * inv_n;
+    int k = 6;
+    for (int a = 0; a < 6; ++a)
+        for (int b = a; b < 6; ++b, ++k) out[k] = (tot[k] - tot[a] * tot[b] * inv_n) * inv_n1;
+}
+
 __global__ void __launch_bounds__(kStatThreads)
-cov6_kernel(SixPtr c, long long n, double* __restrict__ out, CovWorkspace* ws) {
-    double o[6];
-#pragma unroll
-    for (int a = 0; a < 6; ++a) o[a] = c.q[a][0];
+cov6_kernel(SixPtr c, long long n_local, long long chunk, long long n_total, int first_block, Centre6 ctr,
+            double* __restrict__ table, PeerTables peers, unsigned int* ticket, double* __restrict__ out) {
     double v[kCovVals];
 #pragma unroll
     for (int k = 0; k < kCovVals; ++k) v[k] = 0.0;
-    for (long long i = (long long)blockIdx.x * kStatThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kStatThreads) {
+    const long long lo = (long long)blockIdx.x * chunk;
+    const long long hi = (lo + chunk < n_local) ? lo + chunk : n_local;
+    for (long long i = lo + threadIdx.x; i < hi; i += kStatThreads) {
         double d[6];
 #pragma unroll
-        for (int a = 0; a < 6; ++a) d[a] = c.q[a][i] - o[a];
+        for (int a = 0; a < 6; ++a) d[a] = c.q[a][i] - ctr.o[a];
 #pragma unroll
         for (int a = 0; a < 6; ++a) {
             v[a] += d[a];
@@ -192,14 +279,19 @@ cov6_kernel(SixPtr c, long long n, double* __restrict__ out, CovWorkspace* ws) {
             }
         }
     }
-    double tot[kCovVals];
-    if (block_reduce_publish<kCovVals, kCovVals>(v, ws->partial, &ws->ticket[0], tot)) {
-        const double inv_n = 1.0 / (double)n, inv_n1 = 1.0 / (double)(n - 1);
-        for (int a = 0; a < 6; ++a) out[a] = o[a] + tot[a] * inv_n;
-        int k = 6;
-        for (int a = 0; a < 6; ++a)
-            for (int b = a; b < 6; ++b, ++k) out[k] = (tot[k] - tot[a] * tot[b] * inv_n) * inv_n1;
+    block_total<kCovVals, -1>(v);
+    if (threadIdx.x == 0) publish_row<kCovVals>(v, first_block + blockIdx.x, table, peers);
+    if (ticket) {
+        double tot[kCovVals];
+        if (last_block_total<kCovVals, -1>(ticket, table, tot)) finish_cov(tot, n_total, ctr, out);
     }
+}
+
+__global__ void __launch_bounds__(kStatThreads)
+cov_final_kernel(const double* __restrict__ table, long long n_total, Centre6 ctr, double* __restrict__ out) {
+    double tot[kCovVals];
+    table_total<kCovVals, -1>(table, tot);
+    if (threadIdx.x == 0) finish_cov(tot, n_total, ctr, out);
 }
 
 // ---- K5 ---------------------------------------------------------------------------------------
@@ -295,32 +387,138 @@ extern "C" int64_t dfcsr_beam_stats_workspace(void) { return (int64_t)sizeof(Sta
 
 extern "C" int64_t dfcsr_beam_cov_workspace(void) { return (int64_t)sizeof(CovWorkspace); }
 
-extern "C" int dfcsr_beam_cov(const double* d_x, const double* d_px, const double* d_y, const double* d_py,
-                              const double* d_z, const double* d_pz, int64_t n, double* d_out, void* d_workspace,
-                              void* stream) {
-    DFCSR_REQUIRE(d_x && d_px && d_y && d_py && d_z && d_pz && d_out && d_workspace, "null pointer");
+extern "C" int64_t dfcsr_stat_chunk(int64_t n_total) {
+    return n_total <= 0 ? 1 : (n_total + kStatBlocks - 1) / kStatBlocks;
+}
+
+static int peer_tables(const uint64_t* h_peer_tables, int32_t n_peers, PeerTables& pt) {
+    DFCSR_REQUIRE(n_peers >= 0 && n_peers <= DFCSR_MAX_PEERS && (n_peers == 0 || h_peer_tables), "bad peer list");
+    pt.n = n_peers;
+    for (int p = 0; p < DFCSR_MAX_PEERS; ++p)
+        pt.tab[p] = p < n_peers ? reinterpret_cast<double*>(static_cast<uintptr_t>(h_peer_tables[p])) : nullptr;
+    for (int p = 0; p < n_peers; ++p) DFCSR_REQUIRE(pt.tab[p] != nullptr, "null peer table");
+    return DFCSR_OK;
+}
+
+// a shard must consist of whole chunks (the last chunk of the bunch may be short)
+static int check_shard(int64_t n_local, int64_t n_total, int32_t first_block, int32_t n_blocks) {
+    const int64_t chunk = dfcsr_stat_chunk(n_total);
+    DFCSR_REQUIRE(n_total >= 2 && n_local >= 0, "need at least two particles");
+    DFCSR_REQUIRE(first_block >= 0 && n_blocks >= 0 && first_block + n_blocks <= kStatBlocks, "bad block range");
+    const int64_t lo = (int64_t)first_block * chunk, hi = (int64_t)(first_block + n_blocks) * chunk;
+    const int64_t expect = (hi < n_total ? hi : n_total) - (lo < n_total ? lo : n_total);
+    DFCSR_REQUIRE(n_local == expect, "shard size does not match its block range (shards are whole chunks of dfcsr_stat_chunk(n_total) particles)");
+    return DFCSR_OK;
+}
+
+static Centre3 centre3(const double* h) {
+    Centre3 c;
+    c.x = h ? h[0] : 0.0; c.z = h ? h[1] : 0.0; c.p = h ? h[2] : 0.0;
+    return c;
+}
+
+extern "C" int dfcsr_beam_stats(const double* d_x, const double* d_z, const double* d_pz, const double* d_px, int64_t n,
+                                const double* h_centre, double* d_stats, void* d_workspace, void* stream) {
+    DFCSR_REQUIRE(d_x && d_z && d_stats && d_workspace, "null pointer");
     DFCSR_REQUIRE(n >= 2, "need at least two particles");
-    SixPtr c;
-    c.q[0] = d_x; c.q[1] = d_px; c.q[2] = d_y; c.q[3] = d_py; c.q[4] = d_z; c.q[5] = d_pz;
-    long long want = (n + kStatThreads - 1) / kStatThreads;
-    unsigned blocks = (unsigned)(want < kStatBlocks ? want : kStatBlocks);
-    cov6_kernel<<<blocks, kStatThreads, 0, as_stream(stream)>>>(c, n, d_out, static_cast<CovWorkspace*>(d_workspace));
+    cudaStream_t st = as_stream(stream);
+    StatWorkspace* ws = reinterpret_cast<StatWorkspace*>(d_workspace);
+    const long long chunk = dfcsr_stat_chunk(n);
+    PeerTables none;
+    none.n = 0;
+    for (int p = 0; p < DFCSR_MAX_PEERS; ++p) none.tab[p] = nullptr;
+    stats_moments<<<kStatBlocks, kStatThreads, 0, st>>>(d_x, d_z, d_pz, d_px, n, chunk, n, 0, centre3(h_centre),
+                                                         &ws->partial[0][0][0], none, &ws->ticket[0], d_stats);
+    stats_residuals<<<kStatBlocks, kStatThreads, 0, st>>>(d_x, d_z, n, chunk, n, 0, &ws->partial[1][0][0], none,
+                                                           &ws->ticket[1], d_stats);
+    count_launch(2);
+    DFCSR_CUDA_OK(cudaGetLastError());
+    return DFCSR_OK;
+}
+
+extern "C" int dfcsr_beam_stats_partial(int32_t pass, const double* d_x, const double* d_z, const double* d_pz,
+                                        const double* d_px, int64_t n_local, int64_t n_total, int32_t first_block,
+                                        int32_t n_blocks, const double* h_centre, double* d_stats, double* d_table,
+                                        const uint64_t* h_peer_tables, int32_t n_peers, void* stream) {
+    DFCSR_REQUIRE((pass == 0 || pass == 1) && d_table && d_stats, "bad argument");
+    DFCSR_REQUIRE(n_local == 0 || (d_x && d_z), "null pointer");
+    int rc = check_shard(n_local, n_total, first_block, n_blocks);
+    if (rc) return rc;
+    PeerTables pt;
+    rc = peer_tables(h_peer_tables, n_peers, pt);
+    if (rc) return rc;
+    if (n_blocks == 0) return DFCSR_OK;
+    const long long chunk = dfcsr_stat_chunk(n_total);
+    cudaStream_t st = as_stream(stream);
+    if (pass == 0)
+        stats_moments<<<(unsigned)n_blocks, kStatThreads, 0, st>>>(d_x, d_z, d_pz, d_px, n_local, chunk, n_total, first_block,
+                                                                   centre3(h_centre), d_table, pt, nullptr, d_stats);
+    else
+        stats_residuals<<<(unsigned)n_blocks, kStatThreads, 0, st>>>(d_x, d_z, n_local, chunk, n_total, first_block, d_table, pt,
+                                                                     nullptr, d_stats);
     count_launch(1);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;
 }
 
-extern "C" int dfcsr_beam_stats(const double* d_x, const double* d_z, const double* d_pz, int64_t n,
-                                double* d_stats, void* d_workspace, void* stream) {
-    DFCSR_REQUIRE(d_x && d_z && d_stats && d_workspace, "null pointer");
+extern "C" int dfcsr_beam_stats_final(int32_t pass, const double* d_table, int64_t n_total, const double* h_centre,
+                                      int32_t have_pz, int32_t have_px, double* d_stats, void* stream) {
+    DFCSR_REQUIRE((pass == 0 || pass == 1) && d_table && d_stats && n_total >= 2, "bad argument");
+    stats_final_kernel<<<1, kStatThreads, 0, as_stream(stream)>>>(pass, d_table, n_total, centre3(h_centre), have_pz, have_px, d_stats);
+    count_launch(1);
+    DFCSR_CUDA_OK(cudaGetLastError());
+    return DFCSR_OK;
+}
+
+static Centre6 centre6(const double* h) {
+    Centre6 c;
+    for (int a = 0; a < 6; ++a) c.o[a] = h ? h[a] : 0.0;
+    return c;
+}
+
+extern "C" int dfcsr_beam_cov(const double* d_x, const double* d_px, const double* d_y, const double* d_py,
+                              const double* d_z, const double* d_pz, int64_t n, const double* h_centre, double* d_out,
+                              void* d_workspace, void* stream) {
+    DFCSR_REQUIRE(d_x && d_px && d_y && d_py && d_z && d_pz && d_out && d_workspace, "null pointer");
     DFCSR_REQUIRE(n >= 2, "need at least two particles");
-    cudaStream_t st = as_stream(stream);
-    StatWorkspace* ws = reinterpret_cast<StatWorkspace*>(d_workspace);
-    long long want = (n + kStatThreads - 1) / kStatThreads;
-    unsigned blocks = (unsigned)(want < kStatBlocks ? want : kStatBlocks);
-    stats_moments<<<blocks, kStatThreads, 0, st>>>(d_x, d_z, d_pz, n, d_stats, ws);
-    stats_residuals<<<blocks, kStatThreads, 0, st>>>(d_x, d_z, n, d_stats, ws);
-    count_launch(2);
+    SixPtr c;
+    c.q[0] = d_x; c.q[1] = d_px; c.q[2] = d_y; c.q[3] = d_py; c.q[4] = d_z; c.q[5] = d_pz;
+    CovWorkspace* ws = static_cast<CovWorkspace*>(d_workspace);
+    PeerTables none;
+    none.n = 0;
+    for (int p = 0; p < DFCSR_MAX_PEERS; ++p) none.tab[p] = nullptr;
+    cov6_kernel<<<kStatBlocks, kStatThreads, 0, as_stream(stream)>>>(c, n, dfcsr_stat_chunk(n), n, 0, centre6(h_centre),
+                                                                     &ws->partial[0][0], none, &ws->ticket[0], d_out);
+    count_launch(1);
+    DFCSR_CUDA_OK(cudaGetLastError());
+    return DFCSR_OK;
+}
+
+extern "C" int dfcsr_beam_cov_partial(const double* d_x, const double* d_px, const double* d_y, const double* d_py,
+                                      const double* d_z, const double* d_pz, int64_t n_local, int64_t n_total,
+                                      int32_t first_block, int32_t n_blocks, const double* h_centre, double* d_table,
+                                      const uint64_t* h_peer_tables, int32_t n_peers, void* stream) {
+    DFCSR_REQUIRE(d_table, "null table");
+    DFCSR_REQUIRE(n_local == 0 || (d_x && d_px && d_y && d_py && d_z && d_pz), "null pointer");
+    int rc = check_shard(n_local, n_total, first_block, n_blocks);
+    if (rc) return rc;
+    PeerTables pt;
+    rc = peer_tables(h_peer_tables, n_peers, pt);
+    if (rc) return rc;
+    if (n_blocks == 0) return DFCSR_OK;
+    SixPtr c;
+    c.q[0] = d_x; c.q[1] = d_px; c.q[2] = d_y; c.q[3] = d_py; c.q[4] = d_z; c.q[5] = d_pz;
+    cov6_kernel<<<(unsigned)n_blocks, kStatThreads, 0, as_stream(stream)>>>(c, n_local, dfcsr_stat_chunk(n_total), n_total, first_block,
+                                                                            centre6(h_centre), d_table, pt, nullptr, nullptr);
+    count_launch(1);
+    DFCSR_CUDA_OK(cudaGetLastError());
+    return DFCSR_OK;
+}
+
+extern "C" int dfcsr_beam_cov_final(const double* d_table, int64_t n_total, const double* h_centre, double* d_out, void* stream) {
+    DFCSR_REQUIRE(d_table && d_out && n_total >= 2, "bad argument");
+    cov_final_kernel<<<1, kStatThreads, 0, as_stream(stream)>>>(d_table, n_total, centre6(h_centre), d_out);
+    count_launch(1);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;
 }

@@ -24,6 +24,8 @@
 // NGP (nearest grid point) is an extension with no reference counterpart:
 // int64 counts, bit-exact for any order.
 #include <atomic>
+#include <cmath>
+#include <cstring>
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -268,14 +270,15 @@ template <bool kTile>
 __global__ void __launch_bounds__(kTile ? kTileThreads : 256, kTile ? 1 : 4)
 cic_fixed_kernel(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ px,
                  long long n, DepGrid g, Tile t, FixedScales fs, const unsigned long long* __restrict__ wslot,
-                 unsigned long long* __restrict__ count, unsigned long long* __restrict__ vxsum) {
+                 unsigned long long wbits_value, unsigned long long* __restrict__ count,
+                 unsigned long long* __restrict__ vxsum) {
     extern __shared__ unsigned ftile[];
     const int cells = kTile ? t.ni * t.nj : 0;
     if (kTile) {
         for (int c = threadIdx.x; c < 4 * cells; c += blockDim.x) ftile[c] = 0u;
         __syncthreads();
     }
-    const VxScale vs = vx_scale(*wslot, fs);
+    const VxScale vs = vx_scale(wslot ? *wslot : wbits_value, fs);
     const double sc_t = scalbn(1.0, fs.f_tile), sc_g = scalbn(1.0, fs.f_glob);
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -343,6 +346,36 @@ cic_fixed_finish(long long cells, FixedScales fs, const unsigned long long* __re
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (long long)gridDim.x * blockDim.x) {
         count[c] = (double)__double_as_longlong(count[c]) * inv_c;
         vxsum[c] = finite ? (double)__double_as_longlong(vxsum[c]) * inv_v : CUDART_NAN;
+    }
+}
+
+// The all-reduce of a particle-sharded deposit, fused with the conversion: every rank reads the (2, cells) int64 grids of
+// ALL ranks through NVLink peer mappings, adds them (integer adds: exact, any order) and converts to fp64.  Each rank
+// ends up with identical bits, and with the bits a single rank holding all particles would have produced.
+struct PeerQ {
+    const long long* q[DFCSR_MAX_PEERS];
+    int n;
+};
+
+__global__ void __launch_bounds__(256)
+cic_fixed_finish_peers(long long cells, FixedScales fs, unsigned long long wbits, PeerQ peers,
+                       double* __restrict__ count, double* __restrict__ vxsum) {
+    const VxScale vs = vx_scale(wbits, fs);
+    const double inv_c = scalbn(1.0, -fs.f_glob);
+    const double wmax = __longlong_as_double((long long)wbits);
+    const bool finite = wmax < CUDART_INF;      // false for inf and NaN
+    const double inv_v = vs.glob > 0.0 ? 1.0 / vs.glob : 0.0;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (long long)gridDim.x * blockDim.x) {
+        long long a = 0, b = 0;
+#pragma unroll
+        for (int p = 0; p < DFCSR_MAX_PEERS; ++p) {
+            if (p < peers.n) {
+                a += peers.q[p][c];
+                b += peers.q[p][cells + c];
+            }
+        }
+        count[c] = (double)a * inv_c;
+        vxsum[c] = finite ? (double)b * inv_v : CUDART_NAN;
     }
 }
 
@@ -429,6 +462,41 @@ static int bits_for(long long v) {      // smallest b with 2^b > v
 
 static std::atomic<unsigned> g_next_slot{0};
 
+// Scales of the fixed-point grids.  ONE scale for the block-private tiles and the output buffers: every particle's
+// contribution is rounded once, to a grid of 2^-f that depends on the TOTAL particle count only, and everything after
+// that is exact integer addition -- so the result does not depend on how the particles are cut into CTAs, launches or
+// GPUs (a particle-sharded deposit summed over ranks gives the bits of the single-GPU deposit).
+static FixedScales fixed_scales(long long n_total) {
+    FixedScales fs;
+    fs.f_glob = 62 - bits_for(n_total);
+    fs.f_glob = fs.f_glob > 50 ? 50 : fs.f_glob;          // |q| <= 2^50 for the mantissa trick of fixed_add_shared_fma
+    fs.f_tile = fs.f_glob;
+    return fs;
+}
+
+// fixed-point deposit of n particles into the int64 grids c64 / v64 (not zeroed here)
+static int deposit_fixed_accumulate(const double* d_x, const double* d_z, const double* d_px, long long n, long long n_total,
+                                    const DepGrid& g, const unsigned long long* d_wslot, unsigned long long wbits,
+                                    unsigned long long* c64, unsigned long long* v64, bool tiled, cudaStream_t st) {
+    const FixedScales fs = fixed_scales(n_total);
+    if (tiled) {
+        Tile t = make_tile(g.nx, g.nz);
+        const size_t smem = (size_t)2 * t.ni * t.nj * sizeof(double);
+        long long want = (n + kParticlesPerCta - 1) / kParticlesPerCta;
+        unsigned blocks = (unsigned)(want < 148 ? (want < 1 ? 1 : want) : 148);
+        DFCSR_CUDA_OK(cudaFuncSetAttribute(cic_fixed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cic_fixed_kernel<true><<<blocks, kTileThreads, smem, st>>>(d_x, d_z, d_px, n, g, t, fs, d_wslot, wbits, c64, v64);
+    } else {
+        Tile t = {0, 0, 0, 0};
+        long long want = (n + 255) / 256;
+        unsigned blocks = (unsigned)(want < 148LL * 4 ? want : 148LL * 4);
+        cic_fixed_kernel<false><<<blocks, 256, 0, st>>>(d_x, d_z, d_px, n, g, t, fs, d_wslot, wbits, c64, v64);
+    }
+    count_launch(1);
+    DFCSR_CUDA_OK(cudaGetLastError());
+    return DFCSR_OK;
+}
+
 // absmax(px) -> fixed-point deposit -> in-place conversion to fp64 (3 launches)
 static int deposit_fixed(const double* d_x, const double* d_z, const double* d_px, long long n, const DepGrid& g,
                          double* d_count, double* d_vxsum, bool tiled, cudaStream_t st) {
@@ -440,38 +508,28 @@ static int deposit_fixed(const double* d_x, const double* d_z, const double* d_p
         long long want = (n + 2047) / 2048;
         unsigned blocks = (unsigned)(want < 148LL * 8 ? (want < 1 ? 1 : want) : 148LL * 8);
         absmax_kernel<<<blocks, 256, 0, st>>>(d_px, n, slot);
+        count_launch(1);
     }
-    FixedScales fs;
-    fs.f_glob = 62 - bits_for(n);
-    unsigned long long* c64 = reinterpret_cast<unsigned long long*>(d_count);
-    unsigned long long* v64 = reinterpret_cast<unsigned long long*>(d_vxsum);
-    if (tiled) {
-        Tile t = make_tile(g.nx, g.nz);
-        const size_t smem = (size_t)2 * t.ni * t.nj * sizeof(double);
-        long long want = (n + kParticlesPerCta - 1) / kParticlesPerCta;
-        unsigned blocks = (unsigned)(want < 148 ? (want < 1 ? 1 : want) : 148);
-        const long long stride = (long long)blocks * kTileThreads;
-        fs.f_tile = 62 - bits_for(((n + stride - 1) / stride) * kTileThreads);
-        fs.f_tile = fs.f_tile > 50 ? 50 : fs.f_tile;          // |q| <= 2^50 for the mantissa trick of fixed_add_shared_fma
-        fs.f_glob = fs.f_glob > fs.f_tile ? fs.f_tile : fs.f_glob;
-        DFCSR_CUDA_OK(cudaFuncSetAttribute(cic_fixed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cic_fixed_kernel<true><<<blocks, kTileThreads, smem, st>>>(d_x, d_z, d_px, n, g, t, fs, slot, c64, v64);
-    } else {
-        Tile t = {0, 0, 0, 0};
-        fs.f_tile = fs.f_glob;
-        long long want = (n + 255) / 256;
-        unsigned blocks = (unsigned)(want < 148LL * 4 ? want : 148LL * 4);
-        cic_fixed_kernel<false><<<blocks, 256, 0, st>>>(d_x, d_z, d_px, n, g, t, fs, slot, c64, v64);
-    }
+    int rc = deposit_fixed_accumulate(d_x, d_z, d_px, n, n, g, slot, 0ull, reinterpret_cast<unsigned long long*>(d_count),
+                                      reinterpret_cast<unsigned long long*>(d_vxsum), tiled, st);
+    if (rc) return rc;
     {
         const long long cells = (long long)g.nx * g.nz;
         long long want = (cells + 255) / 256;
         unsigned blocks = (unsigned)(want < 148LL * 4 ? want : 148LL * 4);
-        cic_fixed_finish<<<blocks, 256, 0, st>>>(cells, fs, slot, d_count, d_vxsum);
+        cic_fixed_finish<<<blocks, 256, 0, st>>>(cells, fixed_scales(n), slot, d_count, d_vxsum);
+        count_launch(1);
     }
-    count_launch(3);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;
+}
+
+// bit pattern of max|px| as the kernels expect it (NaN / inf / negative input: "not finite" => vxsum becomes NaN)
+static unsigned long long absmax_bits(double absmax_px) {
+    if (!(absmax_px >= 0.0) || std::isinf(absmax_px)) return 0x7ff8000000000000ULL;
+    unsigned long long b;
+    memcpy(&b, &absmax_px, sizeof(b));
+    return b;
 }
 
 }  // namespace dfcsr
@@ -493,7 +551,7 @@ extern "C" int dfcsr_deposit_cic(const double* d_x, const double* d_z, const dou
     if (n == 0) return DFCSR_OK;
     DepGrid g = make_grid(nx, x_start, x_end, nz, z_start, z_end);
     if (mode == 0) mode = (n >= 65536) ? 4 : 5;
-    if (mode >= 4) return deposit_fixed(d_x, d_z, d_px, n, g, d_count, d_vxsum, mode == 4, st);
+    if (mode >= 4) return deposit_fixed(d_x, d_z, d_px, n, g, d_count, d_vxsum, mode == 4, st);   // counts its own launches
     if (mode == 2) {
         long long want = (n + 255) / 256;
         unsigned blocks = (unsigned)(want < 148LL * 8 ? want : 148LL * 8);
@@ -513,6 +571,42 @@ extern "C" int dfcsr_deposit_cic(const double* d_x, const double* d_z, const dou
         else DFCSR_LAUNCH_TILE(false);
 #undef DFCSR_LAUNCH_TILE
     }
+    count_launch(1);
+    DFCSR_CUDA_OK(cudaGetLastError());
+    return DFCSR_OK;
+}
+
+extern "C" int dfcsr_deposit_cic_q(const double* d_x, const double* d_z, const double* d_px, int64_t n_local,
+                                   int64_t n_total, int32_t nx, double x_start, double x_end, int32_t nz, double z_start,
+                                   double z_end, double absmax_px, int64_t* d_q, void* stream) {
+    DFCSR_REQUIRE(d_q && (n_local == 0 || (d_x && d_z && d_px)), "null pointer");
+    DFCSR_REQUIRE(nx >= 1 && nz >= 1 && n_local >= 0 && n_total >= n_local && n_total >= 1, "bad sizes");
+    DFCSR_REQUIRE((long long)nx * nz < (1LL << 30), "grid too large");
+    cudaStream_t st = as_stream(stream);
+    const size_t cells = (size_t)nx * nz;
+    DFCSR_CUDA_OK(cudaMemsetAsync(d_q, 0, 2 * cells * sizeof(int64_t), st));
+    if (n_local == 0) return DFCSR_OK;
+    DepGrid g = make_grid(nx, x_start, x_end, nz, z_start, z_end);
+    unsigned long long* q = reinterpret_cast<unsigned long long*>(d_q);
+    return deposit_fixed_accumulate(d_x, d_z, d_px, n_local, n_total, g, nullptr, absmax_bits(absmax_px), q, q + cells,
+                                    n_local >= 65536, st);
+}
+
+extern "C" int dfcsr_deposit_cic_finish(const uint64_t* h_peer_q, int32_t n_peers, int32_t nx, int32_t nz, int64_t n_total,
+                                        double absmax_px, double* d_count, double* d_vxsum, void* stream) {
+    DFCSR_REQUIRE(h_peer_q && n_peers >= 1 && n_peers <= DFCSR_MAX_PEERS && d_count && d_vxsum, "bad argument");
+    DFCSR_REQUIRE(nx >= 1 && nz >= 1 && n_total >= 1, "bad sizes");
+    PeerQ pq;
+    pq.n = n_peers;
+    for (int p = 0; p < DFCSR_MAX_PEERS; ++p) {
+        pq.q[p] = p < n_peers ? reinterpret_cast<const long long*>(static_cast<uintptr_t>(h_peer_q[p])) : nullptr;
+        DFCSR_REQUIRE(p >= n_peers || pq.q[p] != nullptr, "null peer grid");
+    }
+    const long long cells = (long long)nx * nz;
+    long long want = (cells + 255) / 256;
+    unsigned blocks = (unsigned)(want < 148LL * 4 ? want : 148LL * 4);
+    cic_fixed_finish_peers<<<blocks, 256, 0, as_stream(stream)>>>(cells, fixed_scales(n_total), absmax_bits(absmax_px), pq,
+                                                                  d_count, d_vxsum);
     count_launch(1);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;

@@ -40,7 +40,7 @@ class _Record:
 
 
 class DF_tracker:
-    def __init__(self, input_dic=None, device=None, deposit_mode=0, precision="fp64"):
+    def __init__(self, input_dic=None, device=None, deposit_mode=0, precision="fp64", shards=None):
         """precision: storage format of the history ring — 'fp64' (parity mode, default) or 'fp32'
         (optional mixed-precision mode: fields stored/blended in fp32, everything else fp64)."""
         if precision not in ("fp64", "fp32"):
@@ -75,6 +75,8 @@ class DF_tracker:
         self.history: ops.DeviceHistory | None = None
         self.rebuilds = 0
         self._deposit_scratch = None
+        self._q_scratch = None
+        self.shards = shards           # distributed.ParticleShards when x, z, px are this rank's shard of the bunch
 
     def configure_params(self, xbins=100, zbins=100, xlim=5, zlim=5, filter_order=0, filter_window=0,
                          velocity_threhold=5, upper_limit=None):
@@ -98,7 +100,7 @@ class DF_tracker:
         already computed by Beam.update_status so that the reduction kernels run once per step."""
         x, z, px = self._as_device(x), self._as_device(z), self._as_device(px)
         if stats is None:
-            stats = ops.beam_stats(x, z)
+            stats = ops.beam_stats(x, z, None, px, shards=self.shards)
         sigma_x, sigma_z = float(stats[_lib.S_SIGMA_X]), float(stats[_lib.S_SIGMA_Z])
         xmean, zmean = float(stats[_lib.S_MEAN_X]), float(stats[_lib.S_MEAN_Z])
         self.sigma_x, self.sigma_z, self.xmean, self.zmean = sigma_x, sigma_z, xmean, zmean
@@ -111,8 +113,27 @@ class DF_tracker:
         z_lo, z_hi = zmean - self.zlim * sigma_z, zmean + self.zlim * sigma_z
         if self._deposit_scratch is None or self._deposit_scratch.shape[1:] != (xb, zb):
             self._deposit_scratch = torch.empty((2, xb, zb), dtype=torch.float64, device=self.device)
-        count, vxsum = ops.deposit_cic(x, z, px, xb, x_lo, x_hi, zb, z_lo, z_hi, mode=self.deposit_mode,
-                                       out=self._deposit_scratch)
+        absmax = float(stats[_lib.S_ABSMAX_PX]) if len(stats) > _lib.S_ABSMAX_PX else -1.0
+        if self.shards is not None and self.deposit_mode == 0:
+            # particles sharded over ranks: fixed-point deposit of this rank's shard, then the exact integer sum over the
+            # ranks fused with the conversion to fp64 (reads all ranks' buffers over NVLink; NCCL all-reduce otherwise)
+            if not absmax >= 0.0:
+                raise _lib.DfcsrError("the sharded deposit needs max|px| from the statistics pass (pass px to beam_stats)")
+            q, ptrs = self.shards.q_buffer(xb * zb)
+            ops.deposit_cic_q(x, z, px, self.shards.n_total, xb, x_lo, x_hi, zb, z_lo, z_hi, absmax, q)
+            self.shards.reduce_q(q)
+            count, vxsum = ops.deposit_cic_finish(ptrs, self.shards.n_total, xb, zb, absmax, out=self._deposit_scratch)
+        elif self.deposit_mode == 0 and absmax >= 0.0:
+            # same two stages on one GPU (max|px| came with the statistics: no separate reduction pass over px)
+            if self._q_scratch is None or self._q_scratch.numel() < 2 * xb * zb:
+                self._q_scratch = torch.empty(2 * xb * zb, dtype=torch.int64, device=self.device)
+            import ctypes as C
+            ops.deposit_cic_q(x, z, px, x.numel(), xb, x_lo, x_hi, zb, z_lo, z_hi, absmax, self._q_scratch)
+            count, vxsum = ops.deposit_cic_finish((C.c_uint64 * 1)(self._q_scratch.data_ptr()), x.numel(), xb, zb, absmax,
+                                                  out=self._deposit_scratch)
+        else:
+            count, vxsum = ops.deposit_cic(x, z, px, xb, x_lo, x_hi, zb, z_lo, z_hi, mode=self.deposit_mode,
+                                           out=self._deposit_scratch)
         x_axis, z_axis = Axis.make(x_lo, x_hi, xb), Axis.make(z_lo, z_hi, zb)
         fields, scalars = ops.make_df(count, vxsum, x_axis, z_axis, window, self.filter_order, self.velocity_threhold)
         self._current = _Record(fields, scalars, x_axis, z_axis, t, sigma_x, sigma_z, xmean, zmean)

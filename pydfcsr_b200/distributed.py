@@ -126,3 +126,144 @@ def make_peer_wake_grid(n: int, device: torch.device):
     flag = torch.tensor([ok], dtype=torch.int32, device=device)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     return grid if int(flag[0]) == 1 else None
+
+
+def shard_blocks(rank: int, world: int, blocks: int = 1024):
+    """Chunks [first, first + count) of the particle index space owned by `rank`: the 1024 chunks of the
+    distribution-independent reductions (include/dfcsr_b200.h: DFCSR_STAT_BLOCKS) are dealt out contiguously."""
+    first = (rank * blocks) // world
+    return first, ((rank + 1) * blocks) // world - first
+
+
+class ParticleShards:
+    """Particles sharded over the ranks of one job ("optional: shard particles for K1").
+
+    The reference replicates the particles on every MPI rank (CSR.py:202-307).  Here a rank may hold only the chunks
+    `shard_blocks` gives it; the three places where all particles meet are made exact so that nothing depends on N:
+      * beam statistics / covariance: per-chunk totals in a (1024, NV) table that every rank sums in the same order;
+      * CIC deposit: 64-bit fixed-point grids, added over ranks (integer addition is exact);
+      * wake mesh: already sharded (block split of the reference), results gathered.
+    The tables and grids live in symmetric memory: a rank's kernels store their rows straight into the tables of all ranks
+    (NVLink peer memory) and read the fixed-point grids of all ranks; one device-side barrier separates writers from
+    readers.  Without peer memory (or with world size 1) NCCL all-reduces do the same."""
+
+    STATS_WORDS = 1024 * 8
+    COV_WORDS = 1024 * 27
+
+    def __init__(self, n_total: int, device: torch.device, max_cells: int, rank: int | None = None, world: int | None = None,
+                 use_peers: bool | None = None):
+        from . import _lib
+        self.n_total = int(n_total)
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.device = torch.device(device)
+        self.chunk = int(_lib.lib.dfcsr_stat_chunk(self.n_total))
+        self.first_block, self.n_blocks = shard_blocks(self.rank, self.world, _lib.STAT_BLOCKS)
+        self.lo = min(self.first_block * self.chunk, self.n_total)
+        self.hi = min((self.first_block + self.n_blocks) * self.chunk, self.n_total)
+        self.n_local = self.hi - self.lo
+        self.max_cells = int(max_cells)
+        words = 2 * self.STATS_WORDS + self.COV_WORDS + 2 * 2 * self.max_cells      # two alternating fixed-point buffers
+        self._offsets = {"stats0": 0, "stats1": self.STATS_WORDS, "cov": 2 * self.STATS_WORDS,
+                         "q0": 2 * self.STATS_WORDS + self.COV_WORDS,
+                         "q1": 2 * self.STATS_WORDS + self.COV_WORDS + 2 * self.max_cells}
+        self._q_parity = 0
+        self.handle = None
+        if use_peers is None:
+            use_peers = (self.world > 1 and dist.is_initialized() and dist.get_backend() == "nccl" and self.device.type == "cuda"
+                         and os.environ.get("DFCSR_FUSED_GATHER", "1") != "0"
+                         and int(os.environ.get("LOCAL_WORLD_SIZE", self.world)) == self.world and self.world <= 8)
+        ok = 1
+        if use_peers:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                self.buf = symm.empty(words, dtype=torch.float64, device=self.device)
+                self.buf.zero_()
+                self.handle = symm.rendezvous(self.buf, dist.group.WORLD)
+                self._bases = [int(p) for p in self.handle.buffer_ptrs]
+            except Exception as e:     # noqa: BLE001 - any failure means "no peer memory": NCCL takes over (collectively)
+                ok = 0
+                if self.rank == 0:
+                    import sys
+                    print(f"[pydfcsr_b200] peer memory unavailable for particle shards ({type(e).__name__}: {e}); using NCCL",
+                          file=sys.stderr)
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag[0]) != 1:
+                self.handle = None
+        if self.handle is None:
+            self.buf = torch.zeros(words, dtype=torch.float64, device=self.device)
+            self._bases = [self.buf.data_ptr()]
+        self.mode = "peers" if self.handle is not None else ("nccl" if self.world > 1 else "single")
+
+    def local_slice(self, a):
+        """This rank's particles of a full-bunch array (last axis = particle index)."""
+        return a[..., self.lo:self.hi]
+
+    def _view(self, key, words):
+        o = self._offsets[key]
+        return self.buf[o:o + words]
+
+    def _peer_ptrs(self, key):
+        import ctypes as C
+        if self.mode != "peers":
+            return None
+        return (C.c_uint64 * self.world)(*[b + 8 * self._offsets[key] for b in self._bases])
+
+    def stats_table(self, p):
+        t = self._view(f"stats{p}", self.STATS_WORDS)
+        if self.mode == "nccl":
+            t.zero_()            # rows of the other ranks must be exactly zero for the all-reduce below
+        return t, self._peer_ptrs(f"stats{p}")
+
+    def cov_table(self):
+        self.barrier()           # nothing but this separates two covariance passes: the peers' readers must be done
+        t = self._view("cov", self.COV_WORDS)
+        if self.mode == "nccl":
+            t.zero_()
+        return t, self._peer_ptrs("cov")
+
+    def exchange(self, table):
+        """Make every rank's table complete: a barrier after the peer stores, or an all-reduce (rows are disjoint and the
+        others zero, so the sum is exact)."""
+        if self.mode == "peers":
+            self.handle.barrier(channel=0)
+        elif self.mode == "nccl":
+            dist.all_reduce(table)
+
+    def barrier(self):
+        if self.mode == "peers":
+            self.handle.barrier(channel=0)
+
+    def q_buffer(self, cells):
+        """(int64 view of 2*cells words, addresses of that buffer on all ranks) for this deposit; two buffers alternate."""
+        import ctypes as C
+        if 2 * cells > 2 * self.max_cells:
+            raise ValueError(f"deposit grid of {cells} cells exceeds the {self.max_cells} cells the shard buffers were sized for")
+        key = f"q{self._q_parity}"
+        self._q_parity ^= 1
+        q = self._view(key, 2 * cells).view(torch.int64)
+        if self.mode == "peers":
+            return q, self._peer_ptrs(key)
+        return q, (C.c_uint64 * 1)(q.data_ptr())
+
+    def reduce_q(self, q):
+        if self.mode == "peers":
+            self.handle.barrier(channel=0)
+        elif self.mode == "nccl":
+            dist.all_reduce(q)
+
+    def gather(self, t: torch.Tensor) -> torch.Tensor:
+        """All particles of a sharded 1-D tensor, on every rank (output / debugging; not on the hot path)."""
+        if self.world == 1:
+            return t
+        sizes = []
+        for r in range(self.world):
+            f, c = shard_blocks(r, self.world)
+            sizes.append(min((f + c) * self.chunk, self.n_total) - min(f * self.chunk, self.n_total))
+        pad = max(sizes)
+        send = torch.zeros(pad, dtype=t.dtype, device=t.device)
+        send[:t.numel()] = t
+        recv = torch.empty(self.world * pad, dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(recv, send)
+        return torch.cat([recv[r * pad:r * pad + sizes[r]] for r in range(self.world)])

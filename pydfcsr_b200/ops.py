@@ -78,9 +78,19 @@ class PendingStats:
             pass
 
 
-def beam_stats_async(x: torch.Tensor, z: torch.Tensor, pz: torch.Tensor | None = None) -> PendingStats:
+def _centre(values, n):
+    if values is None:
+        return None
+    return (C.c_double * n)(*[float(v) for v in values])
+
+
+def beam_stats_async(x: torch.Tensor, z: torch.Tensor, pz: torch.Tensor | None = None, px: torch.Tensor | None = None,
+                     centre=None, shards=None) -> PendingStats:
     """Device reductions -> 16 doubles (indices: ``_lib.S_*``) copied to pinned host memory on the current stream.
-    Nothing blocks here: the host can keep enqueueing work and call ``.get()`` when it needs the numbers."""
+    Nothing blocks here: the host can keep enqueueing work and call ``.get()`` when it needs the numbers.
+    centre: (x, z, pz) about which the first pass accumulates (same on every rank; None = zeros).
+    shards: a `distributed.ParticleShards` when x, z, ... are this rank's shard of a bunch distributed over ranks; the
+    result is then the statistics of the WHOLE bunch, bit-identical on every rank and to the single-GPU pass."""
     _ptr(x), _ptr(z)          # raises for non-CUDA tensors before anything is allocated
     dev = x.device
     if dev not in _stats_ws:
@@ -89,9 +99,21 @@ def beam_stats_async(x: torch.Tensor, z: torch.Tensor, pz: torch.Tensor | None =
         _stats_ws[dev] = [torch.zeros(lib.dfcsr_beam_stats_workspace(), dtype=torch.uint8, device=dev), []]
     ws, free = _stats_ws[dev]
     host = free.pop() if free else torch.zeros(_lib.STATS_DOUBLES, dtype=F64).pin_memory()
-    d_stats = torch.empty(_lib.STATS_DOUBLES, dtype=F64, device=dev)
-    check(lib.dfcsr_beam_stats(_ptr(_f64(x, "x")), _ptr(_f64(z, "z")), _ptr(pz), x.numel(), _ptr(d_stats),
-                               _ptr(ws), _stream()), "dfcsr_beam_stats")
+    d_stats = torch.zeros(_lib.STATS_DOUBLES, dtype=F64, device=dev)
+    ctr = _centre(centre, 3)
+    if shards is None:
+        check(lib.dfcsr_beam_stats(_ptr(_f64(x, "x")), _ptr(_f64(z, "z")), _ptr(pz), _ptr(px), x.numel(), ctr, _ptr(d_stats),
+                                   _ptr(ws), _stream()), "dfcsr_beam_stats")
+    else:
+        for p in (0, 1):
+            table, peer_ptrs = shards.stats_table(p)
+            check(lib.dfcsr_beam_stats_partial(p, _ptr(_f64(x, "x")), _ptr(_f64(z, "z")), _ptr(pz), _ptr(px), x.numel(),
+                                               shards.n_total, shards.first_block, shards.n_blocks, ctr, _ptr(d_stats),
+                                               _ptr(table), peer_ptrs, len(peer_ptrs) if peer_ptrs is not None else 0,
+                                               _stream()), "dfcsr_beam_stats_partial")
+            shards.exchange(table)
+            check(lib.dfcsr_beam_stats_final(p, _ptr(table), shards.n_total, ctr, int(pz is not None), int(px is not None),
+                                             _ptr(d_stats), _stream()), "dfcsr_beam_stats_final")
     global _mirror_ok
     if _mirror_ok:      # one-warp store into the mapped pinned buffer: no copy engine, nothing to queue behind
         _mirror_ok = lib.dfcsr_mirror_to_host(_ptr(d_stats), C.c_void_p(host.data_ptr()), _lib.STATS_DOUBLES, _stream()) == 0
@@ -102,24 +124,34 @@ def beam_stats_async(x: torch.Tensor, z: torch.Tensor, pz: torch.Tensor | None =
     return PendingStats(host, ev, free)
 
 
-def beam_stats(x: torch.Tensor, z: torch.Tensor, pz: torch.Tensor | None = None) -> np.ndarray:
+def beam_stats(x: torch.Tensor, z: torch.Tensor, pz: torch.Tensor | None = None, px: torch.Tensor | None = None,
+               centre=None, shards=None) -> np.ndarray:
     """Device reductions -> 16 doubles on the host (indices: ``_lib.S_*``).  Synchronises."""
-    return beam_stats_async(x, z, pz).get()
+    return beam_stats_async(x, z, pz, px, centre, shards).get()
 
 
 _cov_ws: dict = {}
 
 
-def beam_cov(coords) -> tuple[np.ndarray, np.ndarray]:
+def beam_cov(coords, centre=None, shards=None) -> tuple[np.ndarray, np.ndarray]:
     """(means[6], cov[6, 6]) of the six coordinate tensors (x, px, y, py, z, pz); np.cov normalisation (ddof = 1).
-    One device pass + 27 doubles to the host.  Synchronises."""
+    One device pass + 27 doubles to the host.  Synchronises.  centre / shards: as for beam_stats_async."""
     dev = coords[0].device
     if dev not in _cov_ws:
         _cov_ws[dev] = (torch.zeros(lib.dfcsr_beam_cov_workspace(), dtype=torch.uint8, device=dev),
                         torch.zeros(27, dtype=F64, device=dev), torch.zeros(27, dtype=F64).pin_memory())
     ws, d_out, h_out = _cov_ws[dev]
     ptrs = [_ptr(_f64(c, "coords")) for c in coords]
-    check(lib.dfcsr_beam_cov(*ptrs, coords[0].numel(), _ptr(d_out), _ptr(ws), _stream()), "dfcsr_beam_cov")
+    ctr = _centre(centre, 6)
+    if shards is None:
+        check(lib.dfcsr_beam_cov(*ptrs, coords[0].numel(), ctr, _ptr(d_out), _ptr(ws), _stream()), "dfcsr_beam_cov")
+    else:
+        table, peer_ptrs = shards.cov_table()
+        check(lib.dfcsr_beam_cov_partial(*ptrs, coords[0].numel(), shards.n_total, shards.first_block, shards.n_blocks, ctr,
+                                         _ptr(table), peer_ptrs, len(peer_ptrs) if peer_ptrs is not None else 0, _stream()),
+              "dfcsr_beam_cov_partial")
+        shards.exchange(table)
+        check(lib.dfcsr_beam_cov_final(_ptr(table), shards.n_total, ctr, _ptr(d_out), _stream()), "dfcsr_beam_cov_final")
     h_out.copy_(d_out, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     flat = h_out.numpy()
@@ -140,6 +172,27 @@ def deposit_cic(x, z, px, nx, x_start, x_end, nz, z_start, z_end, mode=0, out=No
     check(lib.dfcsr_deposit_cic(_ptr(_f64(x, "x")), _ptr(_f64(z, "z")), _ptr(_f64(px, "px")), x.numel(),
                                 nx, x_start, x_end, nz, z_start, z_end, _ptr(out[0]), _ptr(out[1]), mode,
                                 _stream()), "dfcsr_deposit_cic")
+    return out[0], out[1]
+
+
+def deposit_cic_q(x, z, px, n_total, nx, x_start, x_end, nz, z_start, z_end, absmax_px, q_out):
+    """Stage 1 of the fixed-point deposit (dfcsr_deposit_cic_q): this rank's particles into the (2, nx*nz) int64 buffer
+    `q_out` at the scales of the whole bunch (n_total particles, absmax_px = max |px| over all of them)."""
+    if q_out.dtype != torch.int64 or q_out.numel() < 2 * nx * nz or not q_out.is_contiguous():
+        raise _lib.DfcsrError("q_out must be a contiguous int64 tensor with at least 2*nx*nz elements")
+    check(lib.dfcsr_deposit_cic_q(_ptr(_f64(x, "x")), _ptr(_f64(z, "z")), _ptr(_f64(px, "px")), x.numel(), int(n_total),
+                                  nx, x_start, x_end, nz, z_start, z_end, float(absmax_px), _ptr(q_out), _stream()),
+          "dfcsr_deposit_cic_q")
+    return q_out
+
+
+def deposit_cic_finish(peer_q_ptrs, n_total, nx, nz, absmax_px, out=None, device=None):
+    """Stage 2 (dfcsr_deposit_cic_finish): sum the fixed-point buffers of all ranks (`peer_q_ptrs`: ctypes uint64 array of
+    their addresses in this process) and convert to the fp64 (count, vxsum) grids."""
+    if out is None:
+        out = torch.empty((2, nx, nz), dtype=F64, device=device)
+    check(lib.dfcsr_deposit_cic_finish(peer_q_ptrs, len(peer_q_ptrs), nx, nz, int(n_total), float(absmax_px),
+                                       _ptr(out[0]), _ptr(out[1]), _stream()), "dfcsr_deposit_cic_finish")
     return out[0], out[1]
 
 

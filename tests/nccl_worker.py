@@ -1,4 +1,5 @@
-"""Worker for test_two_rank_nccl_pipeline: CSR2D(parallel=True) on 2 GPUs vs the serial launch."""
+"""Worker for test_two_rank_nccl_pipeline: CSR2D(parallel=True) on 2 GPUs vs the serial launch, with the particles
+replicated on every rank (the reference's layout) and sharded over the ranks (this implementation's default)."""
 import os
 import sys
 
@@ -9,14 +10,20 @@ sys.path.insert(0, ROOT)
 from pydfcsr_b200 import CSR2D, synth  # noqa: E402
 
 elements = [(n, k, L, a, e1, e2, 1) for (n, k, L, a, e1, e2, _s) in synth.CHICANE_ELEMENTS]
-inp = {"input_beam": {"style": "synthetic", "n_particle": 100_000, "seed": 1},
-       "input_lattice": {"lattice_config": synth.chicane_lattice_config(elements=elements)},
-       "particle_deposition": dict(xbins=64, zbins=96, xlim=5, zlim=5, filter_order=1, filter_window=9,
-                                   velocity_threhold=1000, upper_limit=2000),
-       "CSR_integration": dict(n_formation_length=1, zbins=40, xbins=40),
-       "CSR_computation": dict(compute_CSR=1, apply_CSR=0, transverse_on=1, xbins=5, zbins=7, xlim=3, zlim=3,
-                               write_beam=None, write_wakes=False, workdir="/tmp/dfcsr_nccl")}
-csr = CSR2D(inp, parallel=True, verbose=False)
+
+
+def make(parallel, shard, apply_csr):
+    inp = {"input_beam": {"style": "synthetic", "n_particle": 100_000, "seed": 1},
+           "input_lattice": {"lattice_config": synth.chicane_lattice_config(elements=elements)},
+           "particle_deposition": dict(xbins=64, zbins=96, xlim=5, zlim=5, filter_order=1, filter_window=9,
+                                       velocity_threhold=1000, upper_limit=2000),
+           "CSR_integration": dict(n_formation_length=1, zbins=40, xbins=40),
+           "CSR_computation": dict(compute_CSR=1, apply_CSR=apply_csr, transverse_on=1, xbins=5, zbins=7, xlim=3, zlim=3,
+                                   write_beam=None, write_wakes=False, workdir="/tmp/dfcsr_nccl")}
+    return CSR2D(inp, parallel=parallel, verbose=False, shard_particles=shard)
+
+
+csr = make(True, False, 0)                  # particles replicated on every rank, like every MPI rank of the reference
 csr.run(stop_time=0.25)
 par = (csr.dE_dct.clone(), csr.x_kick.clone())
 csr.calculate_2D_CSR()                      # serial launch on this rank, same state
@@ -40,5 +47,30 @@ if csr._peer_grid is not None:
 gathered = [torch.empty_like(par[0]) for _ in range(csr.world_size)]
 torch.distributed.all_gather(gathered, par[0])
 assert all(torch.equal(g, par[0]) for g in gathered), "ranks disagree"
-os.write(1, f"nccl ok {csr.rank} exchange={path}\n".encode())        # one write per rank: print() pieces interleave across ranks
+
+# ---- particles sharded over the ranks: every bit of a run with the kick applied must be the single-GPU run's ----------
+one = make(False, False, 1)                  # this rank alone, all particles
+one.run(stop_time=0.45)
+shd = make(True, True, 1)
+assert shd.beam.shards is not None and shd.beam.x.numel() < one.beam.x.numel()
+shd.run(stop_time=0.45)
+mode = shd.beam.shards.mode
+assert torch.equal(shd.dE_dct, one.dE_dct) and torch.equal(shd.x_kick, one.x_kick), "sharded particles: wake grids differ"
+lo, hi = shd.beam.shards.lo, shd.beam.shards.hi
+for k in range(6):
+    assert torch.equal(shd.beam.coords[k], one.beam.coords[k][lo:hi]), f"sharded particles: coordinate {k} differs"
+st_a, st_b = shd.beam.stats, one.beam.stats
+assert all(float(a) == float(b) for a, b in zip(st_a[:14], st_b[:14])), "sharded particles: statistics differ"
+tw_a, tw_b = shd.beam.twiss, one.beam.twiss
+assert all(tw_a[k] == tw_b[k] for k in tw_b), "sharded particles: Twiss parameters differ"
+full = shd.beam.to_host()
+assert full.shape == (6, one.beam.x.numel()) and (full[0] == one.beam.x.cpu().numpy()).all()
+if mode == "peers":                           # same run through the NCCL fallback of the shard exchange
+    os.environ["DFCSR_FUSED_GATHER"] = "0"
+    alt = make(True, True, 1)
+    assert alt.beam.shards.mode == "nccl"
+    alt.run(stop_time=0.45)
+    assert torch.equal(alt.dE_dct, one.dE_dct) and torch.equal(alt.beam.coords[1], shd.beam.coords[1]), "NCCL shard exchange differs"
+    os.environ["DFCSR_FUSED_GATHER"] = "1"
+os.write(1, f"nccl ok {csr.rank} exchange={path} shards={mode}\n".encode())   # one write per rank: print() pieces interleave
 torch.distributed.destroy_process_group()

@@ -501,3 +501,92 @@ def test_zero_density_skipping_empty_and_full_rows(dev):
             assert n_gat == 0 and n_in == 0 and not de.any() and not kick.any()      # every x' node is dropped up front
         else:
             assert n_gat == n_in > 0 and bool(de.abs().max() > 0)
+
+
+# ---- particle shards: statistics, covariance and deposit must not depend on how the particles are distributed ----
+def _emulated_shards(n, world):
+    """(first_block, n_blocks, lo, hi) of every rank of a `world`-rank job, as distributed.ParticleShards computes them."""
+    from pydfcsr_b200 import _lib
+    from pydfcsr_b200.distributed import shard_blocks
+    chunk = int(_lib.lib.dfcsr_stat_chunk(n))
+    out = []
+    for r in range(world):
+        f, c = shard_blocks(r, world)
+        out.append((f, c, min(f * chunk, n), min((f + c) * chunk, n)))
+    assert out[0][2] == 0 and out[-1][3] == n and all(a[3] == b[2] for a, b in zip(out, out[1:]))
+    return out
+
+
+@pytest.mark.parametrize("n", [1_000_003, 4097])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_statistics_and_covariance_are_independent_of_the_sharding(dev, n, world):
+    """dfcsr_beam_stats / dfcsr_beam_cov on one GPU against the same bunch cut into `world` shards whose chunk totals
+    meet in one table (what N ranks do over NVLink peer memory): every one of the 14 statistics and 27 covariance
+    entries must be BITWISE equal."""
+    import ctypes as C
+    import torch
+    from pydfcsr_b200 import _lib, ops, synth
+    from pydfcsr_b200.ops import _ptr
+    b = synth.gaussian_bunch(n, seed=11, tilt=0.7)
+    b[0] += 3.0e-3
+    coords = [_up(b[k], dev) for k in range(6)]
+    x, px, z, pz = coords[0], coords[1], coords[4], coords[5]
+    centre = [float(b[0][0]), float(b[4][0]), float(b[5][0])]
+    centre6 = [float(b[k][0]) for k in range(6)]
+    ref = ops.beam_stats(x, z, pz, px, centre=centre)
+    rmean, rcov = ops.beam_cov(coords, centre=centre6)
+    assert ref[_lib.S_ABSMAX_PX] == float(np.max(np.abs(b[1]))) and ref[_lib.S_N] == n
+    table = torch.zeros(1024 * 8, dtype=torch.float64, device=dev)
+    ctab = torch.zeros(1024 * 27, dtype=torch.float64, device=dev)
+    d_stats = torch.zeros(16, dtype=torch.float64, device=dev)
+    d_cov = torch.zeros(27, dtype=torch.float64, device=dev)
+    ctr = (C.c_double * 3)(*centre)
+    ctr6 = (C.c_double * 6)(*centre6)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    shards = _emulated_shards(n, world)
+    for p in (0, 1):
+        table.fill_(float("nan"))            # every row must be rewritten by its owner
+        for f, c, lo, hi in shards:
+            _lib.check(_lib.lib.dfcsr_beam_stats_partial(p, _ptr(x[lo:hi]), _ptr(z[lo:hi]), _ptr(pz[lo:hi]), _ptr(px[lo:hi]),
+                                                         hi - lo, n, f, c, ctr, _ptr(d_stats), _ptr(table), None, 0, st))
+        _lib.check(_lib.lib.dfcsr_beam_stats_final(p, _ptr(table), n, ctr, 1, 1, _ptr(d_stats), st))
+    for f, c, lo, hi in shards:
+        _lib.check(_lib.lib.dfcsr_beam_cov_partial(*[_ptr(q[lo:hi]) for q in coords], hi - lo, n, f, c, ctr6, _ptr(ctab), None, 0, st))
+    _lib.check(_lib.lib.dfcsr_beam_cov_final(_ptr(ctab), n, ctr6, _ptr(d_cov), st))
+    got = d_stats.cpu().numpy()
+    assert np.array_equal(got[:14], ref[:14]), (got[:14] - ref[:14])
+    flat = d_cov.cpu().numpy()
+    assert np.array_equal(flat[:6], rmean) and np.array_equal(flat[6:], rcov[np.triu_indices(6)])
+    # and the numbers are the right ones (np.std / np.polyfit / np.cov in fp64 on the host)
+    assert abs(got[_lib.S_SIGMA_X] / np.std(b[0]) - 1) < 1e-11 and abs(got[_lib.S_SLOPE] / np.polyfit(b[4], b[0], 1)[0] - 1) < 1e-10
+    assert np.allclose(rcov, np.cov(b), rtol=1e-9, atol=0)
+
+
+@pytest.mark.parametrize("shape", [(100, 100), (300, 300), (64, 512)])
+@pytest.mark.parametrize("world", [2, 8])
+def test_fixed_point_deposit_is_independent_of_the_sharding(dev, shape, world):
+    """dfcsr_deposit_cic (one GPU, all particles) against dfcsr_deposit_cic_q per shard + dfcsr_deposit_cic_finish over
+    the shards' integer grids: bitwise equal, and equal to the serial oracle within the deposit gate."""
+    import ctypes as C
+    import torch
+    from pydfcsr_b200 import ops, synth
+    n = 600_011
+    b = synth.gaussian_bunch(n, seed=5, tilt=2.5 if shape[0] != shape[1] else 0.0)
+    x, z, px = _up(b[0], dev), _up(b[4], dev), _up(b[1], dev)
+    nx, nz = shape
+    lim = (float(np.mean(b[0]) - 5 * np.std(b[0])), float(np.mean(b[0]) + 5 * np.std(b[0])),
+           float(np.mean(b[4]) - 5 * np.std(b[4])), float(np.mean(b[4]) + 5 * np.std(b[4])))
+    c_ref, v_ref = (t.clone() for t in ops.deposit_cic(x, z, px, nx, lim[0], lim[1], nz, lim[2], lim[3]))
+    amax = float(np.max(np.abs(b[1])))
+    qs = []
+    for f, c, lo, hi in _emulated_shards(n, world):
+        q = torch.empty(2 * nx * nz, dtype=torch.int64, device=dev)
+        ops.deposit_cic_q(x[lo:hi], z[lo:hi], px[lo:hi], n, nx, lim[0], lim[1], nz, lim[2], lim[3], amax, q)
+        qs.append(q)
+    ptrs = (C.c_uint64 * world)(*[q.data_ptr() for q in qs])
+    c_got, v_got = ops.deposit_cic_finish(ptrs, n, nx, nz, amax, device=dev)
+    assert torch.equal(c_got, c_ref) and torch.equal(v_got, v_ref)
+    ref = O.cic_deposit_2d(b[0], b[4], np.ones(n), nx, lim[0], lim[1], nz, lim[2], lim[3])
+    assert _rel(c_got.cpu().numpy(), ref) < 1e-12
+    refv = O.cic_deposit_2d(b[0], b[4], b[1], nx, lim[0], lim[1], nz, lim[2], lim[3])
+    assert _rel(v_got.cpu().numpy(), refv) < 1e-12
