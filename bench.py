@@ -164,7 +164,7 @@ def oracle_state(wl):
         hist.push(fl, wl["integration"]["n_formation_length"])
 
     log(coords, 0, float("inf"))
-    coords = tracking.track_linear(coords, tracking.Drift(0.1)); pos += 0.1
+    coords = tracking.track_exact(coords, tracking.Drift(0.1), 5.0e9); pos += 0.1
     fl = 0.1
     log(coords, pos, fl)
     for k in range(5):
@@ -174,7 +174,7 @@ def oracle_state(wl):
             fl = (24 * R ** 2 * 5 * float(np.std(coords[4]))) ** (1 / 3)
         el = tracking.SBend(L=0.1, G=0.0483 / 0.5002, E1=0.0, E2=0.0,
                             FRINGE_AT="entrance_end" if k == 0 else "no_end")
-        coords = tracking.track_linear(coords, el); pos += 0.1
+        coords = tracking.track_exact(coords, el, 5.0e9); pos += 0.1
         log(coords, pos, fl)
         del last
     x, z = coords[0], coords[4]
@@ -262,6 +262,8 @@ def gpu_arm(args):
     trk = csr.DF_tracker
     trk.pop_right_interpolant()                               # the timed step re-deposits the 0.6 m slice
     beam = csr.beam
+    sharded = beam.shards is not None
+    n_particle_total = beam.n_total
     pristine = [c.clone() for c in beam.coords]
     host = [c.cpu().pin_memory() for c in pristine]
     n_pts = csr.CSR_params.xbins * csr.CSR_params.zbins
@@ -309,8 +311,9 @@ def gpu_arm(args):
         hot_path(False)
         out_host[0].copy_(beam.coords[1], non_blocking=True)
         out_host[1].copy_(beam.coords[5], non_blocking=True)
-        out_host[2][0].copy_(csr.dE_dct, non_blocking=True)
-        out_host[2][1].copy_(csr.x_kick, non_blocking=True)
+        if rank == 0:                                         # every rank holds the same gathered grids: one download
+            out_host[2][0].copy_(csr.dE_dct, non_blocking=True)
+            out_host[2][1].copy_(csr.x_kick, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     # End-to-end loop with the copies taken off the critical path: step k+1's particle batch is uploaded, and
@@ -353,8 +356,9 @@ def gpu_arm(args):
                     continue
                 out_host[0].copy_(dbuf[b][1], non_blocking=True)
                 out_host[1].copy_(dbuf[b][5], non_blocking=True)
-                out_host[2][0].copy_(res[0], non_blocking=True)
-                out_host[2][1].copy_(res[1], non_blocking=True)
+                if rank == 0:
+                    out_host[2][0].copy_(res[0], non_blocking=True)
+                    out_host[2][1].copy_(res[1], non_blocking=True)
         copy_stream.synchronize()
         beam.coords = saved
 
@@ -417,6 +421,7 @@ def gpu_arm(args):
 
     # ---- parity on every line (all ranks take part: the parallel launch is collective) -----------------------------------
     hot_state = _final_state(csr, trk, O, pristine, parallel)
+    strong = None if args.no_strong else strong_scaling_record(world, args.steps, flush)
     if rank != 0:
         return
     peaks = {}
@@ -461,15 +466,21 @@ def gpu_arm(args):
                    "points_per_gpu": n_pts // world,
                    "parallelism": (f"obs-mesh block split x{world} (4096 points per GPU), " +
                                    ("exchange fused into K4 (NVLink peer-memory stores + one barrier)"
-                                    if getattr(csr, "_peer_grid", None) is not None else "NCCL all-gather"))
+                                    if getattr(csr, "_peer_grid", None) is not None else "NCCL all-gather") +
+                                   (f"; particles sharded x{world} (statistics tables + integer deposit grids combined over "
+                                    f"{beam.shards.mode}, bit-identical to one GPU)" if sharded else "; particles replicated"))
                    if parallel else "single GPU"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "k4_ms_per_launch": float(np.mean([a.elapsed_time(b) for a, b in k4_e2e_events])) if k4_e2e_events else None,
                 "ms_per_step_unpipelined": ms_e2e_serial / args.steps,
                 "how": "per step: x, px, z, pz H2D from pinned host memory, hot path, px, pz and both wake grids D2H; "
-                       "copies double-buffered on a second stream (the unpipelined figure serialises them)",
-                "h2d_bytes_per_step": int(sum(host[k].numel() * 8 for k in (0, 1, 4, 5))),
-                "d2h_bytes_per_step": int(out_host[0].numel() * 8 * 2 + out_host[2].numel() * 8)},
+                       "copies double-buffered on a second stream (the unpipelined figure serialises them)" +
+                       ("; the particles are sharded over the ranks, so every rank moves 1/N of the batch, and the wake "
+                        "grids (identical on all ranks) are downloaded by rank 0 only" if sharded else ""),
+                "h2d_bytes_per_step": int(n_particle_total * 8 * 4),
+                "d2h_bytes_per_step": int(n_particle_total * 8 * 2 + out_host[2].numel() * 8),
+                "h2d_bytes_per_step_per_rank": int(sum(host[k].numel() * 8 for k in (0, 1, 4, 5))),
+                "d2h_bytes_per_step_rank0": int(out_host[0].numel() * 8 * 2 + out_host[2].numel() * 8)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "l1", "kernel": "wake_mesh_kernel_p (K4)", "achieved": achieved, "peak": l1_peak,
@@ -488,6 +499,8 @@ def gpu_arm(args):
                              "(DESIGN.md §4, profiles/)"},
         "parity": hot_state["parity"],
     }
+    if strong is not None:
+        line["strong"] = strong
     if probe:
         line["roofline"]["probe"] = probe
     if args.precision != "fp64":
@@ -513,6 +526,99 @@ def gpu_arm(args):
                                 "parity_max_rel_dE": line["parity"]["max_rel_dE"],
                                 "parity_max_rel_kick": line["parity"]["max_rel_kick"]}
     print(json.dumps(line), file=_JSON_OUT, flush=True)
+
+
+STRONG = dict(
+    name="lcls_bc_1e7_mesh128x128_int200x200_fp64",          # BASELINE.json configs[2]: "1e7 particles, 128x128 mesh, sharded over 8xB200"
+    beam=dict(n_particle=10_000_000, seed=0, sigma_z=20.0e-6, chirp=-360.0), position=0.6,
+    mesh=dict(xbins=128, zbins=128, xlim=5, zlim=5),
+)
+
+
+def _one_step(csr, events=None):
+    """One pass of the hot path at the current lattice position (same stages as the headline step)."""
+    import torch
+    b, trk = csr.beam, csr.DF_tracker
+    b.update_status()
+    trk.get_DF(x=b.x, z=b.z, px=b.px, t=b.position, stats=b.stats)
+    trk.append_DF()
+    trk.append_interpolant(formation_length=csr.formation_length, n_formation_length=csr.integration_params.n_formation_length)
+    trk.build_interpolant()
+    csr.get_CSR_mesh()
+    if events is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    if csr.parallel:
+        csr.calculate_2D_CSR_parallel()
+    else:
+        csr.calculate_2D_CSR()
+    if events is not None:
+        ev[1].record()
+        events.append(ev)
+    b.apply_wakes(csr.dE_dct, csr.x_kick, csr.CSR_xrange_transformed, csr.CSR_zrange, 0.1, 1)
+    trk.pop_right_interpolant()
+
+
+def strong_scaling_record(world, steps, flush):
+    """STRONG scaling on BASELINE.json configs[2]: the FIXED 128 x 128 mesh and 1e7 particles, full step (statistics, K1-K5),
+    on the N ranks of this job (mesh block split + particle shards) and, in the same processes, on every rank alone with all
+    particles and the whole mesh (t_1).  Collective; returns the record on every rank."""
+    import torch
+    import torch.distributed as dist
+    from pydfcsr_b200 import CSR2D, synth
+    wl = dict(WORKLOAD, n_particle=STRONG["beam"]["n_particle"], mesh=STRONG["mesh"])
+    inp = _input_dict(wl, world=1)
+    inp["input_beam"] = dict(style="synthetic", **STRONG["beam"])
+    steps = max(3, min(steps, 20))
+
+    def measure(parallel):
+        csr = CSR2D(inp, parallel=parallel, verbose=False)
+        csr.run(stop_time=STRONG["position"] - 0.05)
+        csr.DF_tracker.pop_right_interpolant()
+        pristine = [c.clone() for c in csr.beam.coords]
+        events = []
+
+        def step(ev=None):
+            flush.zero_()
+            csr.beam.coords[1].copy_(pristine[1]); csr.beam.coords[5].copy_(pristine[5])
+            _one_step(csr, ev)
+
+        for _ in range(3):
+            step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(events)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps, float(np.mean([a.elapsed_time(b) for a, b in events]))],
+                          dtype=torch.float64, device=csr.device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        grids = torch.stack([csr.dE_dct, csr.x_kick]).clone()
+        shards = csr.beam.shards.mode if csr.beam.shards is not None else None
+        del csr
+        torch.cuda.empty_cache()
+        return float(ms[0]), float(ms[1]), grids, shards
+
+    t1, k41, g1, _ = measure(False)
+    rec = {"workload": STRONG["name"], "mesh": [STRONG["mesh"]["xbins"], STRONG["mesh"]["zbins"]],
+           "n_particle": STRONG["beam"]["n_particle"], "steps": steps, "t_1_ms": t1, "k4_1_ms": k41,
+           "non_k4_1_ms": t1 - k41,
+           "how": "full step (statistics, K1, K2, K3, K4 + exchange, K5, statistics) with the particles resident, L2 flushed "
+                  "between steps, CUDA events, max over ranks; t_1 = every rank alone with all particles and the whole mesh, "
+                  "measured in the same processes"}
+    if world > 1:
+        tn, k4n, gn, shards = measure(True)
+        rec.update({"n_gpus": world, "t_N_ms": tn, "k4_N_ms": k4n, "non_k4_N_ms": tn - k4n, "speedup": t1 / tn,
+                    "efficiency": t1 / (world * tn), "particles": f"sharded ({shards})" if shards else "replicated",
+                    "grids_bitwise_equal_to_single_gpu": bool(torch.equal(gn, g1))})
+    return rec
 
 
 def _final_state(csr, trk, O, pristine, parallel):
@@ -573,6 +679,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling record (configs[2], 1e7 particles)")
     ap.add_argument("--precision", choices=["fp64", "fp32"], default="fp64",
                     help="history storage: fp64 = parity mode (default, the benchmarked configuration); fp32 = optional mode")
     ap.add_argument("--cpu-points-per-core", type=int, default=256, help="mesh points per host core in the cpu_baseline leg")
@@ -581,7 +688,11 @@ def main():
     # stdout carries exactly ONE line, the JSON record; everything the library prints on the way (the reference's
     # "start reinterpolation" messages, deposit.py:340) goes to stderr
     global _JSON_OUT
-    _JSON_OUT = sys.stdout
+    # ... including what native libraries write to file descriptor 1 (NCCL prints its version there): fd 1 is pointed at
+    # stderr for the whole process and the JSON line goes to a duplicate of the original stdout
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     sys.stdout = sys.stderr
     if args.impl == "reference":
         args.steps = 3 if args.steps is None else args.steps

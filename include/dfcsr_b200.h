@@ -303,10 +303,29 @@ int dfcsr_apply_kick(const double* d_x, const double* d_z, double* d_px, double*
                      const double* d_dE, const double* d_kick, dfcsr_axis x_axis, dfcsr_axis z_axis,
                      double step_size, double init_energy, int32_t transverse_on, void* stream);
 
+/* ---- particle transport through one lattice element (beams.py:101-106: track_element(particle, element)) ----------
+ * In place on the six coordinate arrays (Bmad-X canonical x, px, y, py, z, pz).  The element types are the ones
+ * CSR2D.get_bmadx_element builds (CSR.py:146-199); the maps restate Bmad's: exact drift, sector bend with
+ * "linear_edge" hard-edge kicks at the selected ends and the exact body solution, thick quadrupole (quad_mat2_calc +
+ * low_energy_z_correction), sextupole as drift-kick-drift (csrc/track.cu).  p0c, mc2: reference momentum and rest
+ * energy [eV].  Reproduces the reference's Bmad-X known answers (test/test_BmadX_tracking.ipynb cells 25, 28, 31). */
+typedef enum { DFCSR_ELEM_DRIFT = 0, DFCSR_ELEM_SBEND = 1, DFCSR_ELEM_QUADRUPOLE = 2, DFCSR_ELEM_SEXTUPOLE = 3 } dfcsr_element_kind;
+typedef struct dfcsr_element {
+    int32_t kind;              /* dfcsr_element_kind                                              */
+    int32_t fringe_entrance;   /* sbend: apply the entrance edge kick (FRINGE_AT both_ends / entrance_end) */
+    int32_t fringe_exit;       /* sbend: apply the exit edge kick (FRINGE_AT both_ends / exit_end)         */
+    int32_t n_step;            /* quadrupole: NUM_STEPS (Bmad-X default 1)                        */
+    double L;                  /* length [m]                                                      */
+    double g, e1, e2;          /* sbend: curvature G [1/m], pole-face angles E1, E2 [rad]         */
+    double k1, k2;             /* quadrupole K1 [1/m^2], sextupole K2 [1/m^3]                     */
+} dfcsr_element;
+int dfcsr_track_element(double* d_x, double* d_px, double* d_y, double* d_py, double* d_z, double* d_pz,
+                        int64_t n, const dfcsr_element* el, double p0c, double mc2, void* stream);
+
 /* ---- linear transfer map -------------------------------------------------------
  * v <- M v for every particle, v = (x, px, y, py, z, pz), in place.  h_matrix: 36 HOST doubles, row-major.
- * First-order stand-in for Bmad-X track_element (beams.py:101-102) when that package is absent: drift,
- * sector bend with pole-face rotations, thick quadrupole (pydfcsr_b200/tracking.py builds the matrices). */
+ * First-order option (tracking order "first"; the default is dfcsr_track_element): drift, sector bend with
+ * pole-face rotations, thick quadrupole (pydfcsr_b200/tracking.py builds the matrices). */
 int dfcsr_track_linear(double* d_x, double* d_px, double* d_y, double* d_py, double* d_z, double* d_pz,
                        int64_t n, const double* h_matrix, void* stream);
 

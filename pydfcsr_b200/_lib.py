@@ -48,6 +48,12 @@ class Lattice(C.Structure):
                 ("min_s", C.c_double), ("delta_s", C.c_double), ("d_rho", C.c_void_p), ("d_distance", C.c_void_p)]
 
 
+class Element(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("fringe_entrance", C.c_int32), ("fringe_exit", C.c_int32), ("n_step", C.c_int32),
+                ("L", C.c_double), ("g", C.c_double), ("e1", C.c_double), ("e2", C.c_double), ("k1", C.c_double),
+                ("k2", C.c_double)]
+
+
 class WakeParams(C.Structure):
     _fields_ = [("t", C.c_double), ("sigma_x", C.c_double), ("sigma_z", C.c_double), ("slope0", C.c_double),
                 ("mean_x", C.c_double), ("formation_window", C.c_double), ("csr_scaling", C.c_double),
@@ -96,6 +102,7 @@ SIGNATURES = {
     "dfcsr_wake_point_debug": (C.c_int, [C.POINTER(History), C.POINTER(Lattice), C.POINTER(WakeParams),
                                          _D, _D, _P, _P, _L, _P, _P, _P]),
     "dfcsr_apply_kick": (C.c_int, [_P, _P, _P, _P, _L, _D, _D, _P, _P, Axis, Axis, _D, _D, _I, _P]),
+    "dfcsr_track_element": (C.c_int, [_P, _P, _P, _P, _P, _P, _L, C.POINTER(Element), _D, _D, _P]),
     "dfcsr_track_linear": (C.c_int, [_P, _P, _P, _P, _P, _P, _L, C.POINTER(C.c_double), _P]),
     "dfcsr_sgolay2d": (C.c_int, [_P, _I, _I, _I, _P, _I, _P, _P]),
     "dfcsr_selftest_sqrt": (C.c_int, [_L, C.c_uint64, _D, _D, C.POINTER(C.c_uint64), _P]),

@@ -37,7 +37,7 @@ class Beam:
             self._charge = input_beam["charge"]
             self._init_energy = input_beam["energy"]
         elif self.style == "synthetic":                                # seeded Gaussian (distgen stand-in)
-            kw = {k: v for k, v in input_beam.items() if k not in ("style", "verbose")}
+            kw = {k: v for k, v in input_beam.items() if k not in ("style", "verbose", "tracking_order")}
             n = kw.pop("n_particle")
             coords = synth.gaussian_bunch(n, **kw)
             self._charge = input_beam.get("charge", synth.CHICANE_BEAM["charge"])
@@ -71,6 +71,7 @@ class Beam:
             c = torch.from_numpy(np.ascontiguousarray(coords, dtype=np.float64)).to(self.device)
         self.coords = [c[k].contiguous() for k in range(6)]
         self._init_gamma = self._init_energy / MC2
+        self.tracking_order = input_beam.get("tracking_order", "exact") if self.style == "synthetic" else "exact"
         self.position = 0
         self.step = 0
         self.update_status()
@@ -116,9 +117,10 @@ class Beam:
 
     def track(self, element, step_size, update_step=True):
         """beams.py:101-106.  `element` comes from tracking.make_element: a Bmad-X element when that package is
-        importable (tracked with bmadx.track_element on the device tensors), else a first-order stand-in."""
+        importable (tracked with bmadx.track_element on the device tensors), else an element of pydfcsr_b200.tracking
+        transported by the restated Bmad maps on the device (`tracking_order = "first"`: first-order matrices)."""
         self.coords = [c.contiguous() for c in tracking.track(tuple(self.coords), element, self.position,
-                                                              self._init_energy, MC2)]
+                                                              self._init_energy, MC2, order=self.tracking_order)]
         self.position += step_size
         if update_step:
             self.step += 1

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdfcsr_b200.so")
-SOURCES = ["api.cu", "beam.cu", "deposit.cu", "make_df.cu", "history.cu", "wake.cu", "sgolay2d.cu"]
+SOURCES = ["api.cu", "beam.cu", "deposit.cu", "make_df.cu", "history.cu", "wake.cu", "sgolay2d.cu", "track.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--cudart", "shared"]
 

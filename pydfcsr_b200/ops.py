@@ -524,8 +524,16 @@ def apply_kick(x, z, px, pz, slope, intercept, dE, kick, x_axis: Axis, z_axis: A
 
 
 # ---------------------------------------------------------------------------------------------
-# linear transfer map (tracking stand-in)
+# particle transport (beams.py:101-106)
 # ---------------------------------------------------------------------------------------------
+def track_element(coords, element: _lib.Element, p0c: float, mc2: float) -> None:
+    """Transport the six coordinate tensors (x, px, y, py, z, pz) through one element, in place (dfcsr_track_element)."""
+    ptrs = [_ptr(_f64(c, "coords")) for c in coords]
+    check(lib.dfcsr_track_element(*ptrs, coords[0].numel(), C.byref(element), float(p0c), float(mc2), _stream()),
+          "dfcsr_track_element")
+
+
+
 def track_linear(coords, matrix) -> None:
     """v <- M v in place for the six coordinate tensors (x, px, y, py, z, pz); `matrix` is a host (6, 6) array."""
     m = np.ascontiguousarray(matrix, dtype=np.float64).reshape(36)

@@ -590,3 +590,31 @@ def test_fixed_point_deposit_is_independent_of_the_sharding(dev, shape, world):
     assert _rel(c_got.cpu().numpy(), ref) < 1e-12
     refv = O.cic_deposit_2d(b[0], b[4], b[1], nx, lim[0], lim[1], nz, lim[2], lim[3])
     assert _rel(v_got.cpu().numpy(), refv) < 1e-12
+
+
+def test_track_element_kernel_reproduces_bmadx_known_answers(dev):
+    """dfcsr_track_element (the device tracker CSR2D.run uses) on the reference's Bmad-X known answers
+    (test/test_BmadX_tracking.ipynb cells 25, 28, 31; the numbers live in tests/test_tracking.py) to 1e-12, and on a
+    whole bunch against the host restatement of the same maps for every element type and fringe variant."""
+    import torch
+    from pydfcsr_b200 import synth, tracking
+    from tests.test_tracking import KNOWN, MC2, P0C
+    for name, (element, want) in KNOWN.items():
+        coords = tuple(torch.full((33,), 1e-3, dtype=torch.float64, device=dev) for _ in range(6))
+        got = tracking.track_exact(coords, element, P0C, MC2)
+        for g, w in zip(got, want):
+            g = g.cpu().numpy()
+            assert np.all(g == g[0]) and abs(g[0] - w) <= 1e-12 * abs(w), (name, g[0], w)
+    b = synth.gaussian_bunch(50_001, seed=17, tilt=0.3)
+    b[2] *= 3.0
+    elements = [tracking.Drift(0.37), tracking.SBend(L=0.5002, G=0.0483 / 0.5002, E1=0.0, E2=0.0483),
+                tracking.SBend(L=0.1, G=-0.0483 / 0.5002, E1=-0.0483, E2=0.0, FRINGE_AT="entrance_end"),
+                tracking.SBend(L=0.1, G=0.3, E1=0.1, E2=0.2, FRINGE_AT="no_end"), tracking.SBend(L=0.2, G=0.0),
+                tracking.Quadrupole(L=0.2, K1=1.7), tracking.Quadrupole(L=0.2, K1=-0.9, NUM_STEPS=4), tracking.Sextupole(L=0.1, K2=3.0)]
+    for el in elements:
+        want = tracking.track_exact(tuple(b), el, 5.0e9)
+        dev_coords = tuple(_up(c, dev) for c in b)
+        got = tracking.track_exact(dev_coords, el, 5.0e9)
+        for k in range(6):
+            scale = max(np.max(np.abs(want[k])), 1e-300)
+            assert np.max(np.abs(got[k].cpu().numpy() - want[k])) <= 2e-15 * scale + 1e-21, (el, k)

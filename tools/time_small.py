@@ -46,14 +46,23 @@ for n in (1_000_000, 10_000_000, 50_000_000):
     for shape in ((100, 100), (300, 300), (64, 512)):
         args = (shape[0], -3e-4, 3e-4, shape[1], -1e-3, 1e-3)
         out = torch.empty((2,) + shape, dtype=torch.float64, device="cuda")
-        for mode in (4, 3, 2):
+        for mode in (0, 4, 5, 3, 2):     # 0 = the default (4 for n >= 65536); 4/5 = fixed point tile / direct; 3/2 = fp64 tile / direct
+            if mode == 5 and n > 1_000_000:
+                continue                  # 64-bit L2 reductions on hot cells: only of interest for small bunches
             ms = timeit(lambda: ops.deposit_cic(x, z, px, *args, mode=mode, out=out))
-            report(f"K1 cic n={n:.0e} grid={shape} mode={mode}", ms, 24 * n)
+            report(f"K1 cic n={n:.0e} grid={shape} mode={mode} (absmax + deposit + finish)", ms, 24 * n)
+        # the two-stage path the tracker uses (max|px| comes with the statistics): deposit_q + finish
+        import ctypes as C
+        q = torch.empty(2 * shape[0] * shape[1], dtype=torch.int64, device="cuda")
+        amax = float(px.abs().max())
+        ptr = (C.c_uint64 * 1)(q.data_ptr())
+        ms = timeit(lambda: (ops.deposit_cic_q(x, z, px, n, *args, amax, q), ops.deposit_cic_finish(ptr, n, shape[0], shape[1], amax, out=out)))
+        report(f"K1 cic n={n:.0e} grid={shape} two-stage q + finish", ms, 24 * n)
     ms = timeit(lambda: ops.deposit_ngp(x, z, 100, -3e-4, 3e-4, 100, -1e-3, 1e-3))
     report(f"K1 ngp n={n:.0e} grid=(100, 100)", ms, 16 * n)
     st = torch.zeros(16, dtype=torch.float64, device="cuda")
-    ms = timeit(lambda: ops.beam_stats(x, z, pz))
-    report(f"A14 stats (2 passes + D2H sync) n={n:.0e}", ms, (24 + 16) * n)
+    ms = timeit(lambda: ops.beam_stats(x, z, pz, px))
+    report(f"A14 stats (2 passes incl. max|px| + D2H sync) n={n:.0e}", ms, (32 + 16) * n)
     de = torch.randn((64, 64), generator=g, device="cuda", dtype=torch.float64)
     ms = timeit(lambda: ops.apply_kick(x, z, px, pz, 0.1, 0.0, de, de, Axis.make(-2e-4, 2e-4, 64), Axis.make(-6e-4, 6e-4, 64), 0.1, 5e9, True))
     report(f"K5 kick n={n:.0e}", ms, 48 * n)
@@ -62,9 +71,10 @@ for n in (1_000_000, 10_000_000, 50_000_000):
 for src, dst in (((100, 100), (500, 500)), ((300, 300), (2000, 503)), ((300, 300), (2000, 2000))):
     f = torch.randn((5,) + src, generator=g, device="cuda", dtype=torch.float64)
     out = torch.empty(dst + (6,), dtype=torch.float64, device="cuda")
+    sup = torch.empty((dst[0], 2), dtype=torch.int32, device="cuda")
     ms = timeit(lambda: ops.history_regrid(f, Axis.make(-3e-4, 3e-4, src[0]), Axis.make(-1e-3, 1e-3, src[1]),
-                                           Axis.make(-3.2e-4, 3.1e-4, dst[0]), Axis.make(-1.1e-3, 1e-3, dst[1]), 0.5, out))
-    report(f"K3 regrid {src}->{dst}", ms, dst[0] * dst[1] * 48 + 5 * src[0] * src[1] * 8)
+                                           Axis.make(-3.2e-4, 3.1e-4, dst[0]), Axis.make(-1.1e-3, 1e-3, dst[1]), 0.5, out, sup))
+    report(f"K3 regrid + row support {src}->{dst}", ms, dst[0] * dst[1] * 48 + 5 * src[0] * src[1] * 8)
 
 for shape, win in (((100, 100), 5), ((300, 300), 9), ((64, 512), 9)):
     cnt = torch.rand(shape, generator=g, device="cuda", dtype=torch.float64) * 100
