@@ -135,6 +135,8 @@ __device__ __forceinline__ void finish_moments(const double (&tot)[kStatVals], l
     stats[DFCSR_S_SIGMA_PZ] = have_pz ? sqrt(fmax(tot[6] * inv_n - ep * ep, 0.0)) : 0.0;
     stats[DFCSR_S_N] = (double)n;
     stats[DFCSR_S_ABSMAX_PX] = have_px ? tot[7] : -1.0;
+    stats[14] = 0.0;
+    stats[15] = 0.0;
 }
 
 __device__ __forceinline__ void finish_residuals(const double (&tot)[kStatVals], long long n, double* __restrict__ stats) {
@@ -166,6 +168,7 @@ stats_moments(const double* __restrict__ x, const double* __restrict__ z, const 
     for (int k = 0; k < kStatVals; ++k) v[k] = 0.0;
     const long long lo = (long long)blockIdx.x * chunk;
     const long long hi = (lo + chunk < n_local) ? lo + chunk : n_local;
+#pragma unroll 4
     for (long long i = lo + threadIdx.x; i < hi; i += kStatThreads) {
         double dx = x[i] - c.x, dz = z[i] - c.z;
         v[0] += dx;
@@ -202,6 +205,7 @@ stats_residuals(const double* __restrict__ x, const double* __restrict__ z, long
     for (int k = 0; k < kStatVals; ++k) v[k] = 0.0;
     const long long lo = (long long)blockIdx.x * chunk;
     const long long hi = (lo + chunk < n_local) ? lo + chunk : n_local;
+#pragma unroll 4
     for (long long i = lo + threadIdx.x; i < hi; i += kStatThreads) {
         double zi = z[i];
         double dx = x[i] - mx, dz = zi - mz;

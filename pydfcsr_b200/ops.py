@@ -99,7 +99,7 @@ def beam_stats_async(x: torch.Tensor, z: torch.Tensor, pz: torch.Tensor | None =
         _stats_ws[dev] = [torch.zeros(lib.dfcsr_beam_stats_workspace(), dtype=torch.uint8, device=dev), []]
     ws, free = _stats_ws[dev]
     host = free.pop() if free else torch.zeros(_lib.STATS_DOUBLES, dtype=F64).pin_memory()
-    d_stats = torch.zeros(_lib.STATS_DOUBLES, dtype=F64, device=dev)
+    d_stats = torch.empty(_lib.STATS_DOUBLES, dtype=F64, device=dev)     # all 16 entries are written by the passes
     ctr = _centre(centre, 3)
     if shards is None:
         check(lib.dfcsr_beam_stats(_ptr(_f64(x, "x")), _ptr(_f64(z, "z")), _ptr(pz), _ptr(px), x.numel(), ctr, _ptr(d_stats),
