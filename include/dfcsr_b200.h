@@ -201,13 +201,14 @@ int dfcsr_deposit_cic(const double* d_x, const double* d_z, const double* d_px, 
  *         them = stats[DFCSR_S_ABSMAX_PX] of the statistics pass);
  * _finish adds the buffers of all ranks -- h_peer_q: n_peers HOST entries, addresses valid in this process (NVLink peer
  *         mappings; a single rank passes its own buffer) -- and converts to the fp64 grids of dfcsr_deposit_cic.
+ *         d_count_max (may be NULL): receives max(count) as the bit pattern of the double, for dfcsr_make_df.
  * Integer addition is exact: every rank gets the bits of dfcsr_deposit_cic (mode 4/5) over all particles on one GPU.
  * The caller puts a cross-rank barrier between the two stages and before the buffers are written again. */
 int dfcsr_deposit_cic_q(const double* d_x, const double* d_z, const double* d_px, int64_t n_local, int64_t n_total,
                         int32_t nx, double x_start, double x_end, int32_t nz, double z_start, double z_end,
                         double absmax_px, int64_t* d_q, void* stream);
 int dfcsr_deposit_cic_finish(const uint64_t* h_peer_q, int32_t n_peers, int32_t nx, int32_t nz, int64_t n_total,
-                             double absmax_px, double* d_count, double* d_vxsum, void* stream);
+                             double absmax_px, double* d_count, double* d_vxsum, uint64_t* d_count_max, void* stream);
 
 int dfcsr_deposit_ngp(const double* d_x, const double* d_z, int64_t n,
                       int32_t nx, double x_start, double x_end,
@@ -222,11 +223,12 @@ int dfcsr_deposit_ngp(const double* d_x, const double* d_z, int64_t n,
  *   [0] max(count)  [1] threshold  [2] trapz normalisation  [3] max(density)
  *   [4] mean(vx_x) after the mask fill (= fill value used by the re-gridding, deposit.py:332)
  *   [5] masked mean  [6] number of cells above the second threshold.
+ * d_count_max (may be NULL): max(count) as delivered by dfcsr_deposit_cic_finish; NULL = reduced here (one more launch).
  * d_workspace needs dfcsr_make_df_workspace(nx, nz) bytes. */
 int64_t dfcsr_make_df_workspace(int32_t nx, int32_t nz);
 int dfcsr_make_df(const double* d_count, const double* d_vxsum, dfcsr_axis x_axis, dfcsr_axis z_axis,
                   int32_t window, const double* d_taps, const double* d_edge_lo, const double* d_edge_hi,
-                  double velocity_threshold, double* d_fields, double* d_scalars,
+                  double velocity_threshold, const uint64_t* d_count_max, double* d_fields, double* d_scalars,
                   void* d_workspace, void* stream);
 
 /* ---- A7 / K3 bilinear re-gridding into a history slot (deposit.py:296-309,328-332,379-390) -----

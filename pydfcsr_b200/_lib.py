@@ -84,10 +84,10 @@ SIGNATURES = {
     "dfcsr_beam_cov_final": (C.c_int, [_P, _L, C.POINTER(C.c_double), _P, _P]),
     "dfcsr_deposit_cic": (C.c_int, [_P, _P, _P, _L, _I, _D, _D, _I, _D, _D, _P, _P, _I, _P]),
     "dfcsr_deposit_cic_q": (C.c_int, [_P, _P, _P, _L, _L, _I, _D, _D, _I, _D, _D, _D, _P, _P]),
-    "dfcsr_deposit_cic_finish": (C.c_int, [C.POINTER(C.c_uint64), _I, _I, _I, _L, _D, _P, _P, _P]),
+    "dfcsr_deposit_cic_finish": (C.c_int, [C.POINTER(C.c_uint64), _I, _I, _I, _L, _D, _P, _P, _P, _P]),
     "dfcsr_deposit_ngp": (C.c_int, [_P, _P, _L, _I, _D, _D, _I, _D, _D, _P, _P]),
     "dfcsr_make_df_workspace": (_L, [_I, _I]),
-    "dfcsr_make_df": (C.c_int, [_P, _P, Axis, Axis, _I, _P, _P, _P, _D, _P, _P, _P, _P]),
+    "dfcsr_make_df": (C.c_int, [_P, _P, Axis, Axis, _I, _P, _P, _P, _D, _P, _P, _P, _P, _P]),
     "dfcsr_history_regrid": (C.c_int, [_P, Axis, Axis, Axis, Axis, _D, _P, _I, _P, _P, _P]),
     "dfcsr_history_row_support": (C.c_int, [_P, _I, _I, _I, _P, _P]),
     "dfcsr_history_pack": (C.c_int, [_P, _I, _I, _I, _P, _P]),

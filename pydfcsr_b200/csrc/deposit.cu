@@ -359,12 +359,13 @@ struct PeerQ {
 
 __global__ void __launch_bounds__(256)
 cic_fixed_finish_peers(long long cells, FixedScales fs, unsigned long long wbits, PeerQ peers,
-                       double* __restrict__ count, double* __restrict__ vxsum) {
+                       double* __restrict__ count, double* __restrict__ vxsum, unsigned long long* __restrict__ count_max) {
     const VxScale vs = vx_scale(wbits, fs);
     const double inv_c = scalbn(1.0, -fs.f_glob);
     const double wmax = __longlong_as_double((long long)wbits);
     const bool finite = wmax < CUDART_INF;      // false for inf and NaN
     const double inv_v = vs.glob > 0.0 ? 1.0 / vs.glob : 0.0;
+    double cmax = 0.0;
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (long long)gridDim.x * blockDim.x) {
         long long a = 0, b = 0;
 #pragma unroll
@@ -374,8 +375,14 @@ cic_fixed_finish_peers(long long cells, FixedScales fs, unsigned long long wbits
                 b += peers.q[p][cells + c];
             }
         }
-        count[c] = (double)a * inv_c;
+        const double cv = (double)a * inv_c;
+        count[c] = cv;
         vxsum[c] = finite ? (double)b * inv_v : CUDART_NAN;
+        cmax = fmax(cmax, cv);
+    }
+    if (count_max) {          // max(count) for dfcsr_make_df (deposit.py:183): non-negative doubles order like their bit patterns
+        cmax = warp_max(cmax);
+        if ((threadIdx.x & 31) == 0 && cmax > 0.0) atomicMax(count_max, (unsigned long long)__double_as_longlong(cmax));
     }
 }
 
@@ -593,7 +600,8 @@ extern "C" int dfcsr_deposit_cic_q(const double* d_x, const double* d_z, const d
 }
 
 extern "C" int dfcsr_deposit_cic_finish(const uint64_t* h_peer_q, int32_t n_peers, int32_t nx, int32_t nz, int64_t n_total,
-                                        double absmax_px, double* d_count, double* d_vxsum, void* stream) {
+                                        double absmax_px, double* d_count, double* d_vxsum, uint64_t* d_count_max,
+                                        void* stream) {
     DFCSR_REQUIRE(h_peer_q && n_peers >= 1 && n_peers <= DFCSR_MAX_PEERS && d_count && d_vxsum, "bad argument");
     DFCSR_REQUIRE(nx >= 1 && nz >= 1 && n_total >= 1, "bad sizes");
     PeerQ pq;
@@ -605,8 +613,10 @@ extern "C" int dfcsr_deposit_cic_finish(const uint64_t* h_peer_q, int32_t n_peer
     const long long cells = (long long)nx * nz;
     long long want = (cells + 255) / 256;
     unsigned blocks = (unsigned)(want < 148LL * 4 ? want : 148LL * 4);
+    if (d_count_max) DFCSR_CUDA_OK(cudaMemsetAsync(d_count_max, 0, sizeof(uint64_t), as_stream(stream)));
     cic_fixed_finish_peers<<<blocks, 256, 0, as_stream(stream)>>>(cells, fixed_scales(n_total), absmax_bits(absmax_px), pq,
-                                                                  d_count, d_vxsum);
+                                                                  d_count, d_vxsum,
+                                                                  reinterpret_cast<unsigned long long*>(d_count_max));
     count_launch(1);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;

@@ -14,23 +14,25 @@
 // (scipy/signal/_savitzky_golay.py:244-258,261); both are computed on the
 // host in fp64 for the (window, order) pair and handed in.
 //
-// One launch: a single thread-block cluster (8 CTAs x 512 threads, distributed over 8 SMs).  The
-// grids are at most a few hundred KB and live in L2; the ten dependent phases are separated by
-// cluster barriers (release/acquire at cluster scope) instead of ten kernel launches, and the
-// grid-wide reductions (max, trapezoid sum, masked mean) are two-level and fixed-order, hence
-// bitwise reproducible.  This kernel is latency-bound (~10 barriers); a roofline fraction is not
-// meaningful for it.
-#include <cooperative_groups.h>
+// Three tile kernels + one elementwise kernel, all staged through shared memory (no cluster / grid barriers):
+//   A  per 32 x 32 output tile: the count and normalised-velocity tiles with their filter halos are loaded ONCE into
+//      shared memory, smoothed along x and then along z there, and the raw smoothed density / velocity go out with the
+//      tile's trapezoid sum and maximum; the last tile to finish adds the tile partials in tile order;
+//   B  per tile: normalised density and masked velocity with halo (+1 for np.gradient), the three gradients, their two
+//      smoothing passes, all in shared memory; partial sums for the masked mean of vx_x;
+//   C  elementwise: vx_x below the second threshold is replaced by the masked mean.
+// max(count), which everything depends on, comes with the deposit (dfcsr_deposit_cic_finish) or from a reduction launch.
+// Every output element is produced by the same sequence of operations as scipy / numpy would apply to it (same taps,
+// same order), and every reduction has a fixed order: bitwise reproducible.  100 x 100: 16 CTAs; 300 x 300: 100 CTAs.
+// Latency-bound by construction (a few microseconds per launch); a roofline fraction is not meaningful.
+#include <limits.h>
+#include <math_constants.h>
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace dfcsr {
 
-constexpr int kDfCtas = 8;        // CTAs of the cluster launch (grids up to kClusterCells cells)
-constexpr int kDfMaxCtas = 64;    // CTAs of the cooperative launch used for larger grids
-constexpr int kClusterCells = 16384;
-constexpr int kDfThreads = 512;
+constexpr int kTile = 32;         // output tile edge
+constexpr int kDfThreads = 256;
 constexpr int kMaxWindow = 33;
 constexpr int kPartials = 4;
 
@@ -40,9 +42,10 @@ struct DfOps {   // device-resident Savitzky-Golay operators (uploaded once per 
     const double* edge_hi;   // [window/2][window]
 };
 
-struct DfWorkspace {
-    double partial[8][kDfMaxCtas][kPartials];
-    // followed by 6 scratch planes of nx*nz doubles
+struct DfHeader {
+    unsigned long long cmax_bits;    // max(count) as the bit pattern of a non-negative double (when reduced here)
+    unsigned int ticket[2];
+    double pad[6];
 };
 
 struct DfParams {
@@ -54,26 +57,36 @@ struct DfParams {
     double velocity_threshold;
     double* fields;
     double* scalars;
-    DfWorkspace* ws;
-    double* scratch;
+    DfHeader* hdr;
+    const unsigned long long* cmax_bits;   // where max(count) is found (the header's slot or the deposit's)
+    double* partial;                       // [2][tiles][kPartials]
+    double* t0;                            // raw smoothed density plane
+    double* t1;                            // raw smoothed velocity plane
+    int tiles_x, tiles_z;
 };
 
-// Savitzky-Golay along one axis for element (i, j); `stride` is the element stride of the filtered
-// axis, `n` its length; `at(k)` fetches the k-th sample of the line through (i, j).
+// Savitzky-Golay along one axis for element i of a line of n samples; `at(k)` fetches sample k of the line.
 template <typename Fetch>
-__device__ __forceinline__ double sg_line(const DfOps& ops, int window, int n, int i, Fetch at) {
+__device__ __forceinline__ double sg_line(const double* taps, const double* edge_lo, const double* edge_hi, int window, int n,
+                                          int i, Fetch at) {
     const int half = window >> 1;
     double acc = 0.0;
     if (i < half) {
-        const double* e = ops.edge_lo + i * window;
+        const double* e = edge_lo + i * window;
         for (int k = 0; k < window; ++k) acc = fma(e[k], at(k), acc);
     } else if (i >= n - half) {
-        const double* e = ops.edge_hi + (i - (n - half)) * window;
+        const double* e = edge_hi + (i - (n - half)) * window;
         for (int k = 0; k < window; ++k) acc = fma(e[k], at(n - window + k), acc);
     } else {
-        for (int k = 0; k < window; ++k) acc = fma(ops.taps[k], at(i - half + k), acc);
+        for (int k = 0; k < window; ++k) acc = fma(taps[k], at(i - half + k), acc);
     }
     return acc;
+}
+
+// first sample of the filter support of element i (interior: i - half; clamped at both ends)
+__device__ __forceinline__ int sg_start(int i, int n, int window) {
+    const int s = i - (window >> 1);
+    return s < 0 ? 0 : (s > n - window ? n - window : s);
 }
 
 // np.gradient along one axis with coordinates (numpy/lib/_function_base_impl.py): second-order
@@ -111,9 +124,9 @@ __device__ __forceinline__ double trapz_weight(const Axis& a, int i) {
     return 0.5 * w;
 }
 
-// block-level reduction of NV values (sum or max per slot) -> partial[slot][cta]
+// block totals of NV values (sum, or max where is_max) in thread 0
 template <int NV>
-__device__ __forceinline__ void cta_reduce(double (&v)[NV], const bool (&is_max)[NV], double (*out)[kPartials], int cta) {
+__device__ __forceinline__ void cta_total(double (&v)[NV], const bool (&is_max)[NV]) {
     __shared__ double sm[kDfThreads / 32][kPartials];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -126,183 +139,233 @@ __device__ __forceinline__ void cta_reduce(double (&v)[NV], const bool (&is_max)
         for (int k = 0; k < NV; ++k) {
             double s = sm[0][k];
             for (int w = 1; w < kDfThreads / 32; ++w) s = is_max[k] ? fmax(s, sm[w][k]) : s + sm[w][k];
-            out[cta][k] = s;
+            v[k] = s;
         }
     }
 }
 
-__device__ __forceinline__ double combine(double (*p)[kPartials], int slot, bool is_max) {
-    double s = ((volatile double*)&p[0][slot])[0];
-    for (int c = 1; c < (int)gridDim.x; ++c) {
-        double t = ((volatile double*)&p[c][slot])[0];
-        s = is_max ? fmax(s, t) : s + t;
+// publish this tile's partials; the last tile to arrive returns true in thread 0 (and may then read all partials)
+__device__ __forceinline__ bool publish_and_ticket(const double* v, int nv, double* partial, int tile, int tiles, unsigned int* ticket) {
+    bool last = false;
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < nv; ++k) partial[(size_t)tile * kPartials + k] = v[k];
+        __threadfence();
+        last = (atomicAdd(ticket, 1u) == (unsigned)tiles - 1u);
+        if (last) { __threadfence(); *ticket = 0u; }
     }
-    return s;
+    return last;
 }
 
-struct ClusterSync {   // 8 CTAs on 8 SMs of one GPC: hardware cluster barrier (release/acquire at cluster scope)
-    __device__ __forceinline__ void sync() { cg::this_cluster().sync(); }
-};
-struct GridSync {      // cooperative launch: grid-wide barrier for grids too large for one cluster
-    __device__ __forceinline__ void sync() { cg::this_grid().sync(); }
+struct TileGeom {
+    int i0, i1, j0, j1;        // output tile (inclusive)
+    int r0, r1, c0, c1;        // rows / columns of the smoothing input region (inclusive)
+    int rw, cw;                // region extents
 };
 
-template <typename Sync>
-__device__ __forceinline__ void make_df_body(const DfParams& P, Sync cluster) {
-    const int cta = blockIdx.x;
+__device__ __forceinline__ TileGeom tile_geom(const DfParams& P) {
+    TileGeom g;
+    const int tx = blockIdx.x / P.tiles_z, tz = blockIdx.x - tx * P.tiles_z;
+    g.i0 = tx * kTile; g.i1 = min(g.i0 + kTile, P.ax.n) - 1;
+    g.j0 = tz * kTile; g.j1 = min(g.j0 + kTile, P.az.n) - 1;
+    g.r0 = sg_start(g.i0, P.ax.n, P.window); g.r1 = sg_start(g.i1, P.ax.n, P.window) + P.window - 1;
+    g.c0 = sg_start(g.j0, P.az.n, P.window); g.c1 = sg_start(g.j1, P.az.n, P.window) + P.window - 1;
+    g.rw = g.r1 - g.r0 + 1;
+    g.cw = g.c1 - g.c0 + 1;
+    return g;
+}
+
+// operators to shared memory: taps[w], edge_lo[h][w], edge_hi[h][w]
+__device__ __forceinline__ void load_ops(const DfOps& ops, int window, double* s_taps, double* s_lo, double* s_hi) {
+    const int half = window >> 1;
+    for (int k = threadIdx.x; k < window; k += kDfThreads) s_taps[k] = ops.taps[k];
+    for (int k = threadIdx.x; k < half * window; k += kDfThreads) { s_lo[k] = ops.edge_lo[k]; s_hi[k] = ops.edge_hi[k]; }
+}
+
+// smooth the region `in` (rows r0.., columns c0..; extents rw x cw) along x into `tmp` (tile rows x cw), then along z
+// into out(i, j) for the tile; `emit(i, j, value)` consumes the result
+template <typename Emit>
+__device__ __forceinline__ void smooth_tile(const DfParams& P, const TileGeom& g, const double* in, double* tmp,
+                                            const double* s_taps, const double* s_lo, const double* s_hi, Emit emit) {
+    const int nx = P.ax.n, nz = P.az.n, w = P.window;
+    const int th = g.i1 - g.i0 + 1, tw = g.j1 - g.j0 + 1;
+    for (int e = threadIdx.x; e < th * g.cw; e += kDfThreads) {
+        const int ti = e / g.cw, cc = e - ti * g.cw;
+        tmp[e] = sg_line(s_taps, s_lo, s_hi, w, nx, g.i0 + ti, [&](int k) { return in[(k - g.r0) * g.cw + cc]; });
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < th * tw; e += kDfThreads) {
+        const int ti = e / tw, tj = e - ti * tw;
+        const double v = sg_line(s_taps, s_lo, s_hi, w, nz, g.j0 + tj, [&](int k) { return tmp[ti * g.cw + (k - g.c0)]; });
+        emit(g.i0 + ti, g.j0 + tj, v);
+    }
+    __syncthreads();
+}
+
+// max(count) when the deposit did not deliver it
+__global__ void __launch_bounds__(kDfThreads)
+count_max_kernel(const double* __restrict__ count, int cells, unsigned long long* slot) {
+    double m = 0.0;
+    for (int c = blockIdx.x * kDfThreads + threadIdx.x; c < cells; c += gridDim.x * kDfThreads) m = fmax(m, count[c]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) atomicMax(slot, (unsigned long long)__double_as_longlong(m));
+}
+
+// ---- phase A -----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kDfThreads)
+make_df_phase_a(DfParams P) {
+    extern __shared__ double smem[];
+    const TileGeom g = tile_geom(P);
+    const int nz = P.az.n;
+    const int half = P.window >> 1;
+    double* s_taps = smem;
+    double* s_lo = s_taps + kMaxWindow;
+    double* s_hi = s_lo + half * P.window;
+    double* in_c = s_hi + half * P.window;
+    double* in_v = in_c + g.rw * g.cw;
+    double* tmp = in_v + g.rw * g.cw;
+    load_ops(P.ops, P.window, s_taps, s_lo, s_hi);
+    const double cmax = __longlong_as_double((long long)*P.cmax_bits);
+    const double thr = cmax / P.velocity_threshold;
+    for (int e = threadIdx.x; e < g.rw * g.cw; e += kDfThreads) {
+        const int rr = e / g.cw, cc = e - rr * g.cw;
+        const size_t o = (size_t)(g.r0 + rr) * nz + (g.c0 + cc);
+        const double cn = P.count[o], vs = P.vxsum[o];
+        in_c[e] = cn;
+        in_v[e] = (cn > thr) ? vs / cn : vs;            // deposit.py:184
+    }
+    __syncthreads();
+    double v[2] = {0.0, -CUDART_INF};
+    smooth_tile(P, g, in_c, tmp, s_taps, s_lo, s_hi, [&](int i, int j, double d) {
+        P.t0[(size_t)i * nz + j] = d;
+        v[0] = fma(trapz_weight(P.ax, i) * trapz_weight(P.az, j), d, v[0]);
+        v[1] = fmax(v[1], d);
+    });
+    smooth_tile(P, g, in_v, tmp, s_taps, s_lo, s_hi, [&](int i, int j, double wv) { P.t1[(size_t)i * nz + j] = wv; });
+    const bool mx[2] = {false, true};
+    cta_total<2>(v, mx);
+    const int tiles = P.tiles_x * P.tiles_z;
+    if (publish_and_ticket(v, 2, P.partial, blockIdx.x, tiles, &P.hdr->ticket[0])) {
+        double dsum = 0.0, dmax = -CUDART_INF;
+        for (int t = 0; t < tiles; ++t) {
+            dsum += ((volatile double*)P.partial)[(size_t)t * kPartials + 0];
+            dmax = fmax(dmax, ((volatile double*)P.partial)[(size_t)t * kPartials + 1]);
+        }
+        dmax = dmax / dsum;                              // max of the normalised density
+        P.scalars[0] = cmax;
+        P.scalars[1] = thr;
+        P.scalars[2] = dsum;
+        P.scalars[3] = dmax;
+        P.scalars[7] = dmax / P.velocity_threshold * 8.0;
+    }
+}
+
+// ---- phase B -----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kDfThreads)
+make_df_phase_b(DfParams P) {
+    extern __shared__ double smem[];
+    const TileGeom g = tile_geom(P);
     const int nx = P.ax.n, nz = P.az.n;
     const int cells = nx * nz;
-    const int tid = cta * kDfThreads + threadIdx.x;
-    const int nthreads = (int)gridDim.x * kDfThreads;
-    const DfOps ops = P.ops;
-    const int window = P.window;
-    double* T0 = P.scratch;
-    double* T1 = T0 + cells;
-    double* T2 = T1 + cells;
-    double* U0 = T2 + cells;
-    double* U1 = U0 + cells;
-    double* U2 = U1 + cells;
+    const int half = P.window >> 1;
+    // region of normalised density / masked velocity: the smoothing region widened by one node for np.gradient
+    const int er0 = max(g.r0 - 1, 0), er1 = min(g.r1 + 1, nx - 1), ec0 = max(g.c0 - 1, 0), ec1 = min(g.c1 + 1, nz - 1);
+    const int ecw = ec1 - ec0 + 1, erw = er1 - er0 + 1;
+    double* s_taps = smem;
+    double* s_lo = s_taps + kMaxWindow;
+    double* s_hi = s_lo + half * P.window;
+    double* dn = s_hi + half * P.window;       // erw x ecw
+    double* vm = dn + erw * ecw;
+    double* grad = vm + erw * ecw;             // rw x cw
+    double* tmp = grad + g.rw * g.cw;          // tile rows x cw
+    load_ops(P.ops, P.window, s_taps, s_lo, s_hi);
+    const bool uni_x = axis_uniform(P.ax);
+    const bool uni_z = axis_uniform(P.az);
+    const double thr = P.scalars[1], dsum = P.scalars[2], thr2 = P.scalars[7];
     double* density = P.fields + (size_t)DFCSR_DENSITY * cells;
     double* density_x = P.fields + (size_t)DFCSR_DENSITY_X * cells;
     double* density_z = P.fields + (size_t)DFCSR_DENSITY_Z * cells;
     double* vx = P.fields + (size_t)DFCSR_VX * cells;
     double* vx_x = P.fields + (size_t)DFCSR_VX_X * cells;
-    const double* count = P.count;
-    const double* vxsum = P.vxsum;
-
-    const bool uni_x = axis_uniform(P.ax);
-    const bool uni_z = axis_uniform(P.az);
-
-    // P0: max(count)
-    {
-        double v[1] = {-INFINITY};
-        for (int c = tid; c < cells; c += nthreads) v[0] = fmax(v[0], count[c]);
-        const bool mx[1] = {true};
-        cta_reduce<1>(v, mx, P.ws->partial[0], cta);
+    for (int e = threadIdx.x; e < erw * ecw; e += kDfThreads) {
+        const int rr = e / ecw, cc = e - rr * ecw;
+        const int i = er0 + rr, j = ec0 + cc;
+        const size_t o = (size_t)i * nz + j;
+        const double d = P.t0[o] / dsum;                 // deposit.py:202
+        const double wv = (d <= thr) ? 0.0 : P.t1[o];    // deposit.py:204 (thr in raw-count units: kept)
+        dn[e] = d;
+        vm[e] = wv;
+        if (i >= g.i0 && i <= g.i1 && j >= g.j0 && j <= g.j1) { density[o] = d; vx[o] = wv; }
     }
-    cluster.sync();
-    const double cmax = combine(P.ws->partial[0], 0, true);
-    const double thr = cmax / P.velocity_threshold;
-
-    // P1: Savitzky-Golay along axis 0 (x) of count and of the normalised velocity
-    for (int c = tid; c < cells; c += nthreads) {
-        const int i = c / nz, j = c - i * nz;
-        T0[c] = sg_line(ops, window, nx, i, [&](int k) { return count[k * nz + j]; });
-        T1[c] = sg_line(ops, window, nx, i, [&](int k) {
-            double cn = count[k * nz + j], vs = vxsum[k * nz + j];
-            return (cn > thr) ? vs / cn : vs;
+    __syncthreads();
+    double v[4] = {0.0, 0.0, 0.0, 0.0};        // sum / count of vx_x where density > thr2; sum where == thr2; count where <
+    for (int f = 0; f < 3; ++f) {
+        // gradient field f on the smoothing region: d(density)/dx, d(density)/dz, d(vx)/dx   (deposit.py:212-213)
+        for (int e = threadIdx.x; e < g.rw * g.cw; e += kDfThreads) {
+            const int rr = e / g.cw, cc = e - rr * g.cw;
+            const int i = g.r0 + rr, j = g.c0 + cc;
+            const double* src = (f == 2) ? vm : dn;
+            double gv;
+            if (f == 1) gv = grad_line(P.az, uni_z, j, [&](int k) { return src[(i - er0) * ecw + (k - ec0)]; });
+            else gv = grad_line(P.ax, uni_x, i, [&](int k) { return src[(k - er0) * ecw + (j - ec0)]; });
+            grad[e] = gv;
+        }
+        __syncthreads();
+        double* out = (f == 0) ? density_x : ((f == 1) ? density_z : vx_x);
+        smooth_tile(P, g, grad, tmp, s_taps, s_lo, s_hi, [&](int i, int j, double sv) {
+            out[(size_t)i * nz + j] = sv;
+            if (f == 2) {
+                const double d = dn[(i - er0) * ecw + (j - ec0)];
+                if (d > thr2) { v[0] += sv; v[1] += 1.0; }
+                else if (d < thr2) v[3] += 1.0;
+                else v[2] += sv;                          // == thr2 (or NaN): keeps its own value
+            }
         });
     }
-    cluster.sync();
-
-    // P2: along axis 1 (z); trapezoid normalisation and max of the smoothed density
-    {
-        double v[2] = {0.0, -INFINITY};
-        for (int c = tid; c < cells; c += nthreads) {
-            const int i = c / nz, j = c - i * nz;
-            double d = sg_line(ops, window, nz, j, [&](int k) { return T0[i * nz + k]; });
-            double w = sg_line(ops, window, nz, j, [&](int k) { return T1[i * nz + k]; });
-            density[c] = d;
-            vx[c] = w;
-            v[0] = fma(trapz_weight(P.ax, i) * trapz_weight(P.az, j), d, v[0]);
-            v[1] = fmax(v[1], d);
+    const bool mx[4] = {false, false, false, false};
+    cta_total<4>(v, mx);
+    const int tiles = P.tiles_x * P.tiles_z;
+    double* partial_b = P.partial + (size_t)tiles * kPartials;
+    if (publish_and_ticket(v, 4, partial_b, blockIdx.x, tiles, &P.hdr->ticket[1])) {
+        double s_gt = 0.0, n_gt = 0.0, s_eq = 0.0, n_lt = 0.0;
+        for (int t = 0; t < tiles; ++t) {
+            const volatile double* q = (volatile double*)partial_b + (size_t)t * kPartials;
+            s_gt += q[0]; n_gt += q[1]; s_eq += q[2]; n_lt += q[3];
         }
-        const bool mx[2] = {false, true};
-        cta_reduce<2>(v, mx, P.ws->partial[1], cta);
-    }
-    cluster.sync();
-    const double dsum = combine(P.ws->partial[1], 0, false);
-    const double dmax = combine(P.ws->partial[1], 1, true) / dsum;   // max of the normalised density
-
-    // P3: normalise, zero the velocity where the (normalised) density is below the raw-count threshold
-    for (int c = tid; c < cells; c += nthreads) {
-        double d = density[c] / dsum;
-        density[c] = d;
-        if (d <= thr) vx[c] = 0.0;
-    }
-    cluster.sync();
-
-    // P4: gradients
-    for (int c = tid; c < cells; c += nthreads) {
-        const int i = c / nz, j = c - i * nz;
-        T0[c] = grad_line(P.ax, uni_x, i, [&](int k) { return density[k * nz + j]; });
-        T1[c] = grad_line(P.az, uni_z, j, [&](int k) { return density[i * nz + k]; });
-        T2[c] = grad_line(P.ax, uni_x, i, [&](int k) { return vx[k * nz + j]; });
-    }
-    cluster.sync();
-
-    // P5: smooth the three gradients along axis 0
-    for (int c = tid; c < cells; c += nthreads) {
-        const int i = c / nz, j = c - i * nz;
-        U0[c] = sg_line(ops, window, nx, i, [&](int k) { return T0[k * nz + j]; });
-        U1[c] = sg_line(ops, window, nx, i, [&](int k) { return T1[k * nz + j]; });
-        U2[c] = sg_line(ops, window, nx, i, [&](int k) { return T2[k * nz + j]; });
-    }
-    cluster.sync();
-
-    // P6: ... and along axis 1; masked sum of vx_x over cells above the second threshold
-    const double thr2 = dmax / P.velocity_threshold * 8.0;
-    {
-        double v[2] = {0.0, 0.0};
-        for (int c = tid; c < cells; c += nthreads) {
-            const int i = c / nz, j = c - i * nz;
-            density_x[c] = sg_line(ops, window, nz, j, [&](int k) { return U0[i * nz + k]; });
-            density_z[c] = sg_line(ops, window, nz, j, [&](int k) { return U1[i * nz + k]; });
-            double g = sg_line(ops, window, nz, j, [&](int k) { return U2[i * nz + k]; });
-            vx_x[c] = g;
-            if (density[c] > thr2) { v[0] += g; v[1] += 1.0; }
-        }
-        const bool mx[2] = {false, false};
-        cta_reduce<2>(v, mx, P.ws->partial[2], cta);
-    }
-    cluster.sync();
-    const double msum = combine(P.ws->partial[2], 0, false);
-    const double mcnt = combine(P.ws->partial[2], 1, false);
-    const double mmean = msum / mcnt;
-
-    // P7: fill vx_x below the threshold with the masked mean; total mean = re-gridding fill value
-    {
-        double v[1] = {0.0};
-        for (int c = tid; c < cells; c += nthreads) {
-            double g = vx_x[c];
-            if (density[c] < thr2) { g = mmean; vx_x[c] = g; }
-            v[0] += g;
-        }
-        const bool mx[1] = {false};
-        cta_reduce<1>(v, mx, P.ws->partial[3], cta);
-    }
-    cluster.sync();
-    if (cta == 0 && threadIdx.x == 0) {
-        P.scalars[0] = cmax;
-        P.scalars[1] = thr;
-        P.scalars[2] = dsum;
-        P.scalars[3] = dmax;
-        P.scalars[4] = combine(P.ws->partial[3], 0, false) / (double)cells;
+        const double mmean = s_gt / n_gt;                // deposit.py:235
         P.scalars[5] = mmean;
-        P.scalars[6] = mcnt;
-        P.scalars[7] = thr2;
+        P.scalars[6] = n_gt;
+        // mean of vx_x after the fill of phase C = fill value of the re-gridding (deposit.py:332)
+        P.scalars[4] = (n_lt > 0.0 ? (s_gt + s_eq) + n_lt * mmean : (s_gt + s_eq)) / (double)cells;
     }
 }
 
-__global__ void __cluster_dims__(kDfCtas, 1, 1) __launch_bounds__(kDfThreads, 1) make_df_kernel(DfParams P) {
-    make_df_body(P, ClusterSync());
+// ---- phase C: vx_x[density < thr2] = mean(vx_x[density > thr2])  (deposit.py:233-235) -------------------------------
+__global__ void __launch_bounds__(kDfThreads)
+make_df_phase_c(DfParams P) {
+    const int cells = P.ax.n * P.az.n;
+    const double thr2 = P.scalars[7], mmean = P.scalars[5];
+    const double* density = P.fields + (size_t)DFCSR_DENSITY * cells;
+    double* vx_x = P.fields + (size_t)DFCSR_VX_X * cells;
+    for (int c = blockIdx.x * kDfThreads + threadIdx.x; c < cells; c += gridDim.x * kDfThreads)
+        if (density[c] < thr2) vx_x[c] = mmean;
 }
-
-__global__ void __launch_bounds__(kDfThreads, 1) make_df_kernel_grid(DfParams P) { make_df_body(P, GridSync()); }
 
 }  // namespace dfcsr
 
 using namespace dfcsr;
 
+static long long df_tiles(int nx, int nz) { return (long long)((nx + kTile - 1) / kTile) * ((nz + kTile - 1) / kTile); }
+
 extern "C" int64_t dfcsr_make_df_workspace(int32_t nx, int32_t nz) {
     if (nx < 1 || nz < 1) return 0;
-    return (int64_t)sizeof(DfWorkspace) + (int64_t)6 * nx * nz * (int64_t)sizeof(double);
+    return (int64_t)sizeof(DfHeader) + (int64_t)2 * df_tiles(nx, nz) * kPartials * (int64_t)sizeof(double) +
+           (int64_t)2 * nx * nz * (int64_t)sizeof(double);
 }
 
 extern "C" int dfcsr_make_df(const double* d_count, const double* d_vxsum, dfcsr_axis x_axis, dfcsr_axis z_axis,
                              int32_t window, const double* d_taps, const double* d_edge_lo, const double* d_edge_hi,
-                             double velocity_threshold, double* d_fields, double* d_scalars, void* d_workspace,
-                             void* stream) {
+                             double velocity_threshold, const uint64_t* d_count_max, double* d_fields, double* d_scalars,
+                             void* d_workspace, void* stream) {
     DFCSR_REQUIRE(d_count && d_vxsum && d_fields && d_scalars && d_workspace, "null device pointer");
     DFCSR_REQUIRE(d_taps && (window < 3 || (d_edge_lo && d_edge_hi)), "null operator pointer");
     DFCSR_REQUIRE(window >= 1 && (window & 1), "window must be odd and positive");
@@ -314,7 +377,9 @@ extern "C" int dfcsr_make_df(const double* d_count, const double* d_vxsum, dfcsr
                   "grid smaller than the filter window");
     DFCSR_REQUIRE((long long)x_axis.n * z_axis.n < (1LL << 30), "grid too large");
     cudaStream_t st = as_stream(stream);
-    DfWorkspace* ws = reinterpret_cast<DfWorkspace*>(d_workspace);
+    const long long cells = (long long)x_axis.n * z_axis.n;
+    const long long tiles = df_tiles(x_axis.n, z_axis.n);
+    char* ws = reinterpret_cast<char*>(d_workspace);
     DfParams P;
     P.count = d_count;
     P.vxsum = d_vxsum;
@@ -327,18 +392,36 @@ extern "C" int dfcsr_make_df(const double* d_count, const double* d_vxsum, dfcsr
     P.velocity_threshold = velocity_threshold;
     P.fields = d_fields;
     P.scalars = d_scalars;
-    P.ws = ws;
-    P.scratch = reinterpret_cast<double*>(reinterpret_cast<char*>(d_workspace) + sizeof(DfWorkspace));
-    const long long cells = (long long)x_axis.n * z_axis.n;
-    if (cells <= kClusterCells) {
-        make_df_kernel<<<kDfCtas, kDfThreads, 0, st>>>(P);
+    P.hdr = reinterpret_cast<DfHeader*>(ws);
+    P.partial = reinterpret_cast<double*>(ws + sizeof(DfHeader));
+    P.t0 = P.partial + 2 * tiles * kPartials;
+    P.t1 = P.t0 + cells;
+    P.tiles_x = (x_axis.n + kTile - 1) / kTile;
+    P.tiles_z = (z_axis.n + kTile - 1) / kTile;
+    DFCSR_CUDA_OK(cudaMemsetAsync(P.hdr, 0, sizeof(DfHeader), st));      // tickets and the max slot
+    int launches = 3;
+    if (d_count_max) {
+        P.cmax_bits = reinterpret_cast<const unsigned long long*>(d_count_max);
     } else {
-        long long want = (cells + 2047) / 2048;
-        int ctas = (int)(want < kDfCtas ? kDfCtas : (want > kDfMaxCtas ? kDfMaxCtas : want));
-        void* args[] = {&P};
-        DFCSR_CUDA_OK(cudaLaunchCooperativeKernel((const void*)make_df_kernel_grid, dim3(ctas), dim3(kDfThreads), args, 0, st));
+        P.cmax_bits = &P.hdr->cmax_bits;
+        long long want = (cells + kDfThreads - 1) / kDfThreads;
+        count_max_kernel<<<(unsigned)(want < 64 ? want : 64), kDfThreads, 0, st>>>(d_count, (int)cells, &P.hdr->cmax_bits);
+        ++launches;
     }
-    count_launch(1);
+    const int half = window >> 1;
+    const int reg = kTile + 2 * half;                  // largest smoothing-region edge
+    const size_t ops_words = kMaxWindow + 2 * (size_t)half * window;
+    const size_t smem_a = (ops_words + 2 * (size_t)reg * reg + (size_t)kTile * reg) * sizeof(double);
+    const size_t smem_b = (ops_words + 2 * (size_t)(reg + 2) * (reg + 2) + (size_t)reg * reg + (size_t)kTile * reg) * sizeof(double);
+    DFCSR_CUDA_OK(cudaFuncSetAttribute(make_df_phase_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    DFCSR_CUDA_OK(cudaFuncSetAttribute(make_df_phase_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    make_df_phase_a<<<(unsigned)tiles, kDfThreads, smem_a, st>>>(P);
+    make_df_phase_b<<<(unsigned)tiles, kDfThreads, smem_b, st>>>(P);
+    {
+        long long want = (cells + kDfThreads - 1) / kDfThreads;
+        make_df_phase_c<<<(unsigned)(want < 148LL * 4 ? want : 148LL * 4), kDfThreads, 0, st>>>(P);
+    }
+    count_launch(launches);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;
 }

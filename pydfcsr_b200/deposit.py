@@ -76,6 +76,7 @@ class DF_tracker:
         self.rebuilds = 0
         self._deposit_scratch = None
         self._q_scratch = None
+        self._count_max = None
         self.shards = shards           # distributed.ParticleShards when x, z, px are this rank's shard of the bunch
 
     def configure_params(self, xbins=100, zbins=100, xlim=5, zlim=5, filter_order=0, filter_window=0,
@@ -114,6 +115,9 @@ class DF_tracker:
         if self._deposit_scratch is None or self._deposit_scratch.shape[1:] != (xb, zb):
             self._deposit_scratch = torch.empty((2, xb, zb), dtype=torch.float64, device=self.device)
         absmax = float(stats[_lib.S_ABSMAX_PX]) if len(stats) > _lib.S_ABSMAX_PX else -1.0
+        cmax = None                     # device slot with max(count) when the deposit delivers it
+        if self._count_max is None:
+            self._count_max = torch.zeros(1, dtype=torch.int64, device=self.device)
         if self.shards is not None and self.deposit_mode == 0:
             # particles sharded over ranks: fixed-point deposit of this rank's shard, then the exact integer sum over the
             # ranks fused with the conversion to fp64 (reads all ranks' buffers over NVLink; NCCL all-reduce otherwise)
@@ -122,7 +126,9 @@ class DF_tracker:
             q, ptrs = self.shards.q_buffer(xb * zb)
             ops.deposit_cic_q(x, z, px, self.shards.n_total, xb, x_lo, x_hi, zb, z_lo, z_hi, absmax, q)
             self.shards.reduce_q(q)
-            count, vxsum = ops.deposit_cic_finish(ptrs, self.shards.n_total, xb, zb, absmax, out=self._deposit_scratch)
+            count, vxsum = ops.deposit_cic_finish(ptrs, self.shards.n_total, xb, zb, absmax, out=self._deposit_scratch,
+                                                  count_max=self._count_max)
+            cmax = self._count_max
         elif self.deposit_mode == 0 and absmax >= 0.0:
             # same two stages on one GPU (max|px| came with the statistics: no separate reduction pass over px)
             if self._q_scratch is None or self._q_scratch.numel() < 2 * xb * zb:
@@ -130,12 +136,14 @@ class DF_tracker:
             import ctypes as C
             ops.deposit_cic_q(x, z, px, x.numel(), xb, x_lo, x_hi, zb, z_lo, z_hi, absmax, self._q_scratch)
             count, vxsum = ops.deposit_cic_finish((C.c_uint64 * 1)(self._q_scratch.data_ptr()), x.numel(), xb, zb, absmax,
-                                                  out=self._deposit_scratch)
+                                                  out=self._deposit_scratch, count_max=self._count_max)
+            cmax = self._count_max
         else:
             count, vxsum = ops.deposit_cic(x, z, px, xb, x_lo, x_hi, zb, z_lo, z_hi, mode=self.deposit_mode,
                                            out=self._deposit_scratch)
         x_axis, z_axis = Axis.make(x_lo, x_hi, xb), Axis.make(z_lo, z_hi, zb)
-        fields, scalars = ops.make_df(count, vxsum, x_axis, z_axis, window, self.filter_order, self.velocity_threhold)
+        fields, scalars = ops.make_df(count, vxsum, x_axis, z_axis, window, self.filter_order, self.velocity_threhold,
+                                      count_max=cmax)
         self._current = _Record(fields, scalars, x_axis, z_axis, t, sigma_x, sigma_z, xmean, zmean)
         self.t = t
 

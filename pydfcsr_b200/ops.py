@@ -186,13 +186,14 @@ def deposit_cic_q(x, z, px, n_total, nx, x_start, x_end, nz, z_start, z_end, abs
     return q_out
 
 
-def deposit_cic_finish(peer_q_ptrs, n_total, nx, nz, absmax_px, out=None, device=None):
+def deposit_cic_finish(peer_q_ptrs, n_total, nx, nz, absmax_px, out=None, device=None, count_max=None):
     """Stage 2 (dfcsr_deposit_cic_finish): sum the fixed-point buffers of all ranks (`peer_q_ptrs`: ctypes uint64 array of
-    their addresses in this process) and convert to the fp64 (count, vxsum) grids."""
+    their addresses in this process) and convert to the fp64 (count, vxsum) grids.  count_max: optional 1-element int64
+    CUDA tensor that receives max(count) (bit pattern of the double) for make_df."""
     if out is None:
         out = torch.empty((2, nx, nz), dtype=F64, device=device)
     check(lib.dfcsr_deposit_cic_finish(peer_q_ptrs, len(peer_q_ptrs), nx, nz, int(n_total), float(absmax_px),
-                                       _ptr(out[0]), _ptr(out[1]), _stream()), "dfcsr_deposit_cic_finish")
+                                       _ptr(out[0]), _ptr(out[1]), _ptr(count_max), _stream()), "dfcsr_deposit_cic_finish")
     return out[0], out[1]
 
 
@@ -230,8 +231,9 @@ _sg_dev: dict = {}
 
 
 def make_df(count, vxsum, x_axis: Axis, z_axis: Axis, window: int, order: int, velocity_threshold: float,
-            out: torch.Tensor | None = None):
-    """(fields[5, nx, nz], scalars[8]) from the deposit grids (deposit.py:183-235)."""
+            out: torch.Tensor | None = None, count_max: torch.Tensor | None = None):
+    """(fields[5, nx, nz], scalars[8]) from the deposit grids (deposit.py:183-235).  count_max: the 1-element int64 CUDA
+    tensor filled by deposit_cic_finish (saves the reduction launch)."""
     nx, nz = x_axis.n, z_axis.n
     dev = count.device
     need = lib.dfcsr_make_df_workspace(nx, nz)
@@ -247,7 +249,8 @@ def make_df(count, vxsum, x_axis: Axis, z_axis: Axis, window: int, order: int, v
                              for a in savgol_operators(window, order))
     taps, lo, hi = _sg_dev[key]
     check(lib.dfcsr_make_df(_ptr(count), _ptr(vxsum), x_axis, z_axis, window, _ptr(taps), _ptr(lo), _ptr(hi),
-                            float(velocity_threshold), _ptr(out), _ptr(scalars), _ptr(ws), _stream()), "dfcsr_make_df")
+                            float(velocity_threshold), _ptr(count_max), _ptr(out), _ptr(scalars), _ptr(ws), _stream()),
+          "dfcsr_make_df")
     return out, scalars
 
 
