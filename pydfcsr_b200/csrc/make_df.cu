@@ -27,6 +27,7 @@
 // Latency-bound by construction (a few microseconds per launch); a roofline fraction is not meaningful.
 #include <limits.h>
 #include <math_constants.h>
+#include <atomic>
 #include "common.cuh"
 
 namespace dfcsr {
@@ -106,6 +107,36 @@ __device__ __forceinline__ double grad_line(const Axis& a, bool uniform, int i, 
     double cb = (h_hi - h_lo) / (h_lo * h_hi);
     double cc = h_lo / (h_hi * (h_lo + h_hi));
     return __dadd_rn(__dadd_rn(__dmul_rn(ca, at(i - 1)), __dmul_rn(cb, at(i))), __dmul_rn(cc, at(i + 1)));
+}
+
+// np.gradient's three-point coefficients of node i (the divisions are per node, not per grid cell): value =
+// ca f(lo) + cb f(mid) + cc f(hi) with (lo, mid, hi) = (i-1, i, i+1), or the one-sided / uniform variants of grad_line
+// expressed in the same form.  kind: 0 = three-term rounded sum (non-uniform interior), 1 = (f(hi) - f(lo)) / den.
+struct GradCoef {
+    double ca, cb, cc;     // kind 0: coefficients; kind 1: cc = denominator
+    int lo, hi, kind;
+};
+
+__device__ __forceinline__ GradCoef grad_coef(const Axis& a, bool uniform, int i) {
+    GradCoef g;
+    const int n = a.n;
+    g.ca = g.cb = 0.0;
+    if (i == 0) { g.lo = 0; g.hi = 1; g.kind = 1; g.cc = axis_node(a, 1) - axis_node(a, 0); return g; }
+    if (i == n - 1) { g.lo = n - 2; g.hi = n - 1; g.kind = 1; g.cc = axis_node(a, n - 1) - axis_node(a, n - 2); return g; }
+    g.lo = i - 1; g.hi = i + 1;
+    if (uniform) { g.kind = 1; g.cc = 2.0 * (axis_node(a, 1) - axis_node(a, 0)); return g; }
+    const double xm = axis_node(a, i - 1), x0 = axis_node(a, i), xp = axis_node(a, i + 1);
+    const double h_lo = x0 - xm, h_hi = xp - x0;
+    g.kind = 0;
+    g.ca = -(h_hi) / (h_lo * (h_lo + h_hi));
+    g.cb = (h_hi - h_lo) / (h_lo * h_hi);
+    g.cc = h_lo / (h_hi * (h_lo + h_hi));
+    return g;
+}
+
+__device__ __forceinline__ double grad_apply(const GradCoef& g, double f_lo, double f_mid, double f_hi) {
+    if (g.kind == 1) return (f_hi - f_lo) / g.cc;
+    return __dadd_rn(__dadd_rn(__dmul_rn(g.ca, f_lo), __dmul_rn(g.cb, f_mid)), __dmul_rn(g.cc, f_hi));
 }
 
 __device__ __forceinline__ bool axis_uniform(const Axis& a) {
@@ -277,9 +308,15 @@ make_df_phase_b(DfParams P) {
     double* vm = dn + erw * ecw;
     double* grad = vm + erw * ecw;             // rw x cw
     double* tmp = grad + g.rw * g.cw;          // tile rows x cw
+    GradCoef* gcx = reinterpret_cast<GradCoef*>(tmp + (g.i1 - g.i0 + 1) * g.cw);     // rw entries
+    GradCoef* gcz = gcx + g.rw;                                                      // cw entries
     load_ops(P.ops, P.window, s_taps, s_lo, s_hi);
     const bool uni_x = axis_uniform(P.ax);
     const bool uni_z = axis_uniform(P.az);
+    for (int e = threadIdx.x; e < g.rw + g.cw; e += kDfThreads) {
+        if (e < g.rw) gcx[e] = grad_coef(P.ax, uni_x, g.r0 + e);
+        else gcz[e - g.rw] = grad_coef(P.az, uni_z, g.c0 + (e - g.rw));
+    }
     const double thr = P.scalars[1], dsum = P.scalars[2], thr2 = P.scalars[7];
     double* density = P.fields + (size_t)DFCSR_DENSITY * cells;
     double* density_x = P.fields + (size_t)DFCSR_DENSITY_X * cells;
@@ -305,8 +342,15 @@ make_df_phase_b(DfParams P) {
             const int i = g.r0 + rr, j = g.c0 + cc;
             const double* src = (f == 2) ? vm : dn;
             double gv;
-            if (f == 1) gv = grad_line(P.az, uni_z, j, [&](int k) { return src[(i - er0) * ecw + (k - ec0)]; });
-            else gv = grad_line(P.ax, uni_x, i, [&](int k) { return src[(k - er0) * ecw + (j - ec0)]; });
+            if (f == 1) {
+                const GradCoef c = gcz[cc];
+                const double* row = src + (i - er0) * ecw - ec0;
+                gv = grad_apply(c, row[c.lo], row[j], row[c.hi]);
+            } else {
+                const GradCoef c = gcx[rr];
+                const double* col = src + (j - ec0) - er0 * ecw;
+                gv = grad_apply(c, col[c.lo * ecw], col[i * ecw], col[c.hi * ecw]);
+            }
             grad[e] = gv;
         }
         __syncthreads();
@@ -412,9 +456,19 @@ extern "C" int dfcsr_make_df(const double* d_count, const double* d_vxsum, dfcsr
     const int reg = kTile + 2 * half;                  // largest smoothing-region edge
     const size_t ops_words = kMaxWindow + 2 * (size_t)half * window;
     const size_t smem_a = (ops_words + 2 * (size_t)reg * reg + (size_t)kTile * reg) * sizeof(double);
-    const size_t smem_b = (ops_words + 2 * (size_t)(reg + 2) * (reg + 2) + (size_t)reg * reg + (size_t)kTile * reg) * sizeof(double);
-    DFCSR_CUDA_OK(cudaFuncSetAttribute(make_df_phase_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
-    DFCSR_CUDA_OK(cudaFuncSetAttribute(make_df_phase_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    const size_t smem_b = (ops_words + 2 * (size_t)(reg + 2) * (reg + 2) + (size_t)reg * reg + (size_t)kTile * reg) * sizeof(double) +
+                          2 * (size_t)reg * sizeof(GradCoef);
+    // opt in to more than 48 KB of dynamic shared memory only when a window needs it, and only once per size (the call
+    // costs several microseconds, as much as one of these kernels)
+    static std::atomic<size_t> granted_a{48 * 1024}, granted_b{48 * 1024};
+    if (smem_a > granted_a.load()) {
+        DFCSR_CUDA_OK(cudaFuncSetAttribute(make_df_phase_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+        granted_a.store(smem_a);
+    }
+    if (smem_b > granted_b.load()) {
+        DFCSR_CUDA_OK(cudaFuncSetAttribute(make_df_phase_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+        granted_b.store(smem_b);
+    }
     make_df_phase_a<<<(unsigned)tiles, kDfThreads, smem_a, st>>>(P);
     make_df_phase_b<<<(unsigned)tiles, kDfThreads, smem_b, st>>>(P);
     {

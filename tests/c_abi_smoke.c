@@ -65,7 +65,7 @@ int main(void) {
         CHECK(dfcsr_deposit_cic_q(dx, dz, dp, n0, n, nx, -1.2e-4, 1.2e-4, nz, -3.6e-4, 3.6e-4, amax, (int64_t*)dq0, NULL));
         CHECK(dfcsr_deposit_cic_q(dx + n0, dz + n0, dp + n0, n1, n, nx, -1.2e-4, 1.2e-4, nz, -3.6e-4, 3.6e-4, amax, (int64_t*)dq1, NULL));
         uint64_t peers[2] = {(uint64_t)(uintptr_t)dq0, (uint64_t)(uintptr_t)dq1};
-        CHECK(dfcsr_deposit_cic_finish(peers, 2, nx, nz, n, amax, dcount2, dvx2, NULL));
+        CHECK(dfcsr_deposit_cic_finish(peers, 2, nx, nz, n, amax, dcount2, dvx2, NULL, NULL));
         double* hcount2 = malloc(nx * nz * 8); double* hvx = malloc(nx * nz * 8); double* hvx2 = malloc(nx * nz * 8);
         cudaMemcpy(hcount2, dcount2, nx * nz * 8, cudaMemcpyDeviceToHost);
         cudaMemcpy(hvx, dvx, nx * nz * 8, cudaMemcpyDeviceToHost); cudaMemcpy(hvx2, dvx2, nx * nz * 8, cudaMemcpyDeviceToHost);
