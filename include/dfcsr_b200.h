@@ -277,12 +277,14 @@ int dfcsr_wake_grid(const dfcsr_history* hist, const dfcsr_lattice* lat, const d
  * collective then distributes, the kernel stores both results of every observation point of this rank's block
  * straight into the wake grid of EVERY rank through NVLink peer mappings: h_peer_grids holds n_peers HOST entries,
  * entry p = the address, valid in THIS process (CUDA IPC / symmetric-memory mapping; this rank's own entry is its
- * local buffer), of rank p's (2, x_axis.n * z_axis.n) fp64 grid [dE | kick]; point k of the block lands at index
- * first + k of both halves.  The caller orders the launch after the peers' last readers of those grids and publishes
+ * local buffer), of rank p's (2, x_axis.n * z_axis.n) fp64 grid [dE | kick]; point k of the launch is mesh point
+ * first + k * stride and lands at that index of both halves.  stride = 1 with the reference's count/displ gives the
+ * contiguous blocks of CSR.py:121-125; first = rank, stride = n_ranks deals the points out round-robin, which balances
+ * ranks whose blocks would hold different numbers of in-grid samples (the gathered grid is bitwise the same).  The caller orders the launch after the peers' last readers of those grids and publishes
  * completion with a barrier across ranks (pydfcsr_b200/distributed.py: two alternating grids + one barrier per step). */
 int dfcsr_wake_grid_peers(const dfcsr_history* hist, const dfcsr_lattice* lat, const dfcsr_wake_params* wp,
                           dfcsr_axis x_axis, dfcsr_axis z_axis, double slope, double intercept,
-                          int64_t first, int64_t count, const uint64_t* h_peer_grids, int32_t n_peers,
+                          int64_t first, int64_t count, int64_t stride, const uint64_t* h_peer_grids, int32_t n_peers,
                           unsigned long long* d_counters, void* stream);
 
 /* 1 if the wake launches above would use zero-density skipping for this history and these beam scalars (row-support

@@ -49,6 +49,11 @@ class CSR2D:
         if shard_particles is None:
             shard_particles = os.environ.get("DFCSR_SHARD_PARTICLES", "1") != "0"
         self.shard_particles = bool(shard_particles) and bool(parallel)
+        # how the observation mesh is dealt out to the ranks when the exchange is fused into the wake kernel: "interleaved"
+        # (point k to rank k mod P: equal work everywhere) or "block" (the reference's contiguous count/displ blocks,
+        # CSR.py:121-125, whose cost differs from rank to rank with the number of in-grid samples).  Same grid bits either
+        # way; the NCCL all-gather path always uses the reference's blocks.
+        self.mesh_split = os.environ.get("DFCSR_MESH_SPLIT", "interleaved")
         self.timestamp = isotime()
         self.verbose = verbose
         self.parallel = bool(parallel)
@@ -321,9 +326,14 @@ class CSR2D:
         peer = getattr(self, "_peer_grid", None)
         if peer is not None:
             grid, ptrs, handle = peer.next()
+            if self.mesh_split == "interleaved":      # points rank, rank + P, ...: equal work on every rank
+                first, stride = self.rank, self.world_size
+                count = (n - self.rank + self.world_size - 1) // self.world_size
+            else:                                     # the reference's contiguous blocks (CSR.py:121-125)
+                first, stride, count = int(self.displ[self.rank]), 1, int(self.count[self.rank])
             try:
                 ops.wake_grid_peers(self.DF_tracker.history, lat, self._wake_params(), xa, za, *self._mesh_slope,
-                                    first=int(self.displ[self.rank]), count=int(self.count[self.rank]), peer_ptrs=ptrs,
+                                    first=first, count=count, stride=stride, peer_ptrs=ptrs,
                                     counters=getattr(self, "wake_counters", None))
             except _lib.DfcsrError as e:
                 # The launch was refused before anything ran (e.g. a shared-memory or slice-size limit).  Every rank

@@ -473,12 +473,12 @@ def wake_grid(hist: DeviceHistory, lat: DeviceLattice, wp: _lib.WakeParams, x_ax
 
 
 def wake_grid_peers(hist: DeviceHistory, lat: DeviceLattice, wp: _lib.WakeParams, x_axis: Axis, z_axis: Axis, slope,
-                    intercept, first, count, peer_ptrs, counters=None):
-    """K4 fused with the exchange (dfcsr_wake_grid_peers): block [first, first+count) of the mesh is computed here and
-    stored into every rank's (2, N) grid; `peer_ptrs` = ctypes array of the grids' addresses as mapped in this process."""
+                    intercept, first, count, peer_ptrs, counters=None, stride=1):
+    """K4 fused with the exchange (dfcsr_wake_grid_peers): mesh points first, first + stride, ... (count of them) are
+    computed here and stored into every rank's (2, N) grid; `peer_ptrs` = ctypes array of the grids' addresses as mapped in this process."""
     hv, lv = hist.view(), lat.view()
     check(lib.dfcsr_wake_grid_peers(C.byref(hv), C.byref(lv), C.byref(wp), x_axis, z_axis, float(slope), float(intercept),
-                                    int(first), int(count), peer_ptrs, len(peer_ptrs), _ptr(counters), _stream()),
+                                    int(first), int(count), int(stride), peer_ptrs, len(peer_ptrs), _ptr(counters), _stream()),
           "dfcsr_wake_grid_peers")
 
 

@@ -424,6 +424,14 @@ def test_fused_exchange_kernel_on_one_gpu(dev):
         ops.wake_grid_peers(hist, dlat, wp, xa, za, slope, icpt, first=displ[r], count=count[r], peer_ptrs=ptrs)
     for g in grids:
         assert torch.equal(g[0], de) and torch.equal(g[1], kick)
+    # the same points dealt out round-robin (mesh point k to rank k mod 3), the default of CSR2D's fused exchange
+    for g in grids:
+        g.fill_(float("nan"))
+    for r in range(world):
+        ops.wake_grid_peers(hist, dlat, wp, xa, za, slope, icpt, first=r, count=(n - r + world - 1) // world, stride=world,
+                            peer_ptrs=ptrs)
+    for g in grids:
+        assert torch.equal(g[0], de) and torch.equal(g[1], kick)
 
 
 def test_fused_sqrt_is_bitwise_the_library_sqrt(dev):
