@@ -296,7 +296,7 @@ def gpu_arm(args):
         if timed_k4:
             ev[1].record()
             (k4_events if sink is None else sink).append(ev)
-        b.apply_wakes(csr.dE_dct, csr.x_kick, csr.CSR_xrange_transformed, csr.CSR_zrange, 0.1, 1)
+        b.apply_wakes(csr.dE_dct, csr.x_kick, csr._mesh_axes[0], csr._mesh_axes[1], 0.1, 1)
         trk.pop_right_interpolant()
 
     def step_resident(timed_k4=False):
@@ -555,7 +555,7 @@ def _one_step(csr, events=None):
     if events is not None:
         ev[1].record()
         events.append(ev)
-    b.apply_wakes(csr.dE_dct, csr.x_kick, csr.CSR_xrange_transformed, csr.CSR_zrange, 0.1, 1)
+    b.apply_wakes(csr.dE_dct, csr.x_kick, csr._mesh_axes[0], csr._mesh_axes[1], 0.1, 1)
     trk.pop_right_interpolant()
 
 

@@ -105,9 +105,12 @@ class Beam:
         """The 16 doubles of `dfcsr_beam_stats` for the current particle state (blocks until they have arrived).
         Reading them also moves the centre of the next first pass to the current means -- a deterministic rule (it follows
         the program order, not the timing), identical on every rank and for every way of sharding the particles."""
-        st = self._pending_stats.get()
-        self._centre = [float(st[_lib.S_MEAN_X]), float(st[_lib.S_MEAN_Z]), float(st[_lib.S_MEAN_PZ])]
-        return st
+        p = self._pending_stats
+        if p._value is None:              # first read of this pass
+            st = p.get()
+            self._centre = [float(st[_lib.S_MEAN_X]), float(st[_lib.S_MEAN_Z]), float(st[_lib.S_MEAN_PZ])]
+            return st
+        return p._value
 
     _sigma_x = property(lambda self: float(self.stats[_lib.S_SIGMA_X]))
     _sigma_z = property(lambda self: float(self.stats[_lib.S_SIGMA_Z]))
@@ -130,8 +133,8 @@ class Beam:
         """beams.py:108-131 on the device, in place."""
         dE = dE_dct if isinstance(dE_dct, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(dE_dct)).to(self.device)
         kick = x_kick if isinstance(x_kick, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x_kick)).to(self.device)
-        xa = Axis.make(xrange[0], xrange[-1], len(xrange))
-        za = Axis.make(zrange[0], zrange[-1], len(zrange))
+        xa = xrange if isinstance(xrange, Axis) else Axis.make(xrange[0], xrange[-1], len(xrange))
+        za = zrange if isinstance(zrange, Axis) else Axis.make(zrange[0], zrange[-1], len(zrange))
         ops.apply_kick(self.x, self.z, self.coords[1], self.coords[5], self._slope[0], self._slope[1],
                        dE.contiguous(), kick.contiguous(), xa, za, step_size, self.init_energy, transverse_on)
         self.update_status()

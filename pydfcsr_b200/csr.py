@@ -199,7 +199,7 @@ class CSR2D:
         else:
             self.calculate_2D_CSR()
         if apply:
-            b.apply_wakes(self.dE_dct, self.x_kick, self.CSR_xrange_transformed, self.CSR_zrange,
+            b.apply_wakes(self.dE_dct, self.x_kick, self._mesh_axes[0], self._mesh_axes[1],
                           kick_length, self.CSR_params.transverse_on)
 
     def run(self, stop_time=None, debug=False):
@@ -256,7 +256,7 @@ class CSR2D:
                     else:
                         self.calculate_2D_CSR()
                     if self.CSR_params.apply_CSR:
-                        b.apply_wakes(self.dE_dct, self.x_kick, self.CSR_xrange_transformed, self.CSR_zrange,
+                        b.apply_wakes(self.dE_dct, self.x_kick, self._mesh_axes[0], self._mesh_axes[1],
                                       DL * lat.nsep[ele_count], self.CSR_params.transverse_on)
                     wb = self.CSR_params.write_beam
                     if wb == "all" or (isinstance(wb, list) and step_count in wb):
@@ -280,13 +280,25 @@ class CSR2D:
         (`dfcsr_wake_grid`), so nothing O(N) is built or uploaded per step.  `CSR_xmesh` / `CSR_zmesh`
         remain available as lazily evaluated host arrays."""
         b, p = self.beam, self.CSR_params
-        sig_x, mean_x = b.sigma_x_transform, b.mean_x_transform
-        self.CSR_zrange = np.linspace(b.mean_z - p.zlim * b.sigma_z, b.mean_z + p.zlim * b.sigma_z, p.zbins)
-        self.CSR_xrange_transformed = np.linspace(mean_x - p.xlim * sig_x, mean_x + p.xlim * sig_x, p.xbins)
-        self._mesh_slope = (float(b._slope[0]), float(b._slope[1]))
-        self._mesh_axes = (Axis.make(self.CSR_xrange_transformed[0], self.CSR_xrange_transformed[-1], p.xbins),
-                           Axis.make(self.CSR_zrange[0], self.CSR_zrange[-1], p.zbins))
+        st = b.stats
+        sig_x, mean_x = float(st[_lib.S_SIGMA_XT]), float(st[_lib.S_MEAN_XT])
+        mean_z, sig_z = float(st[_lib.S_MEAN_Z]), float(st[_lib.S_SIGMA_Z])
+        # np.linspace(a, b, n)[0] is a and [-1] is b exactly: the axes need only the end points (the arrays are lazy)
+        self._mesh_ends = (mean_x - p.xlim * sig_x, mean_x + p.xlim * sig_x, mean_z - p.zlim * sig_z, mean_z + p.zlim * sig_z)
+        self._mesh_slope = (float(st[_lib.S_SLOPE]), float(st[_lib.S_INTERCEPT]))
+        self._mesh_axes = (Axis.make(self._mesh_ends[0], self._mesh_ends[1], p.xbins),
+                           Axis.make(self._mesh_ends[2], self._mesh_ends[3], p.zbins))
         self._mesh_host = None
+        self._ranges_host = None
+
+    def _ranges(self):
+        if self._ranges_host is None:
+            e, p = self._mesh_ends, self.CSR_params
+            self._ranges_host = (np.linspace(e[0], e[1], p.xbins), np.linspace(e[2], e[3], p.zbins))
+        return self._ranges_host
+
+    CSR_xrange_transformed = property(lambda self: self._ranges()[0])
+    CSR_zrange = property(lambda self: self._ranges()[1])
 
     def _mesh_arrays(self):
         if self._mesh_host is None:
