@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import distributed as dist_utils
-from . import _lib, ops, tracking
+from . import _lib, ops, outputs, tracking
 from ._lib import Axis
 from .beams import Beam
 from .deposit import DF_tracker
@@ -378,9 +378,11 @@ class CSR2D:
         return float(de[0]), float(kick[0])
 
     # ------------------------------------------------------------------------------- output
-    # The reference writes HDF5 (CSR.py:784-879); h5py is not available offline, so the same
-    # content goes to .npz files with the same group/dataset names flattened into keys.
+    # The reference's files (CSR.py:784-879), written through the same create_group / create_dataset / attrs calls with
+    # the same names.  The container is HDF5 when h5py is importable, else an .npz with the same tree (outputs.py).
     def dump_beam(self, label):
+        """CSR.py:784-797.  The reference writes an openPMD file through pmd_beamphysics (absent offline); here the six
+        Bmad-X coordinates and the beam scalars go to one store (collective when the particles are sharded)."""
         if not getattr(self.CSR_params, "write_beam", None):
             return
         coords = self.beam.to_host() if (self.beam.shards is not None or self.rank == 0) else None   # collective if sharded
@@ -388,29 +390,60 @@ class CSR2D:
             return
         path = full_path(self.CSR_params.workdir)
         os.makedirs(path, exist_ok=True)
-        fn = os.path.join(path, f"{self.prefix}-particles-{label}.npz")
-        np.savez(fn, coords=coords, position=self.beam.position, charge=self.beam.charge,
-                 energy=self.beam.init_energy)
+        fn = outputs.store_path(os.path.join(path, f"{self.prefix}-particles-{label}"))
+        if os.path.isfile(fn):
+            os.remove(fn)
+        with outputs.open_store(fn, "w") as hf:
+            for k, name in enumerate(("x", "px", "y", "py", "z", "pz")):
+                hf.create_dataset(name, data=coords[k])
+            hf.attrs["position"] = self.beam.position
+            hf.attrs["charge"] = self.beam.charge
+            hf.attrs["p0c"] = self.beam.init_energy
+            hf.attrs["coordinates"] = "Bmad-X canonical (x, px, y, py, z, pz)"
         self._log("Beam at position {} is written to {}".format(self.beam.position, fn))
 
     def write_wakes(self):
+        """CSR.py:799-835: one group per CSR step, step_k/{longitudinal,transverse}/{x_grids,z_grids,dE_dct|xkicks}."""
         if self.rank != 0:
             return
         path = full_path(self.CSR_params.workdir)
         os.makedirs(path, exist_ok=True)
-        step = self.beam.step
+        fn = outputs.store_path(os.path.join(path, f"{self.prefix}-wakes"))
+        if self.beam.step == 1 and os.path.isfile(fn):
+            os.remove(fn)
         shape = tuple(self.dE_dct.shape)
-        np.savez(os.path.join(path, f"{self.prefix}-wakes-step_{step}.npz"),
-                 step=step, position=self.beam.position, charge=self.beam.charge,
-                 x_grids=self.CSR_xmesh.reshape(shape), z_grids=self.CSR_zmesh.reshape(shape),
-                 dE_dct=self.dE_dct.cpu().numpy(), xkicks=self.x_kick.cpu().numpy(), unit="MeV/m")
+        with outputs.open_store(fn, "a") as hf:
+            step = self.beam.step
+            g = hf.create_group("step_" + str(step))
+            g.attrs["step"] = step
+            g.attrs["position"] = self.beam.position
+            g.attrs["mean_gamma"] = self.beam.init_gamma
+            g.attrs["beam_energy"] = self.beam.init_energy
+            g.attrs["element"] = str(self.lattice.current_element)
+            g.attrs["charge"] = self.beam.charge
+            g1 = g.create_group("longitudinal")
+            g1.attrs["unit"] = "MeV/m"
+            g1.create_dataset("x_grids", data=self.CSR_xmesh.reshape(shape))
+            g1.create_dataset("z_grids", data=self.CSR_zmesh.reshape(shape))
+            g1.create_dataset("dE_dct", data=self.dE_dct.cpu().numpy())
+            g2 = g.create_group("transverse")
+            g2.attrs["unit"] = "MeV/m"
+            g2.create_dataset("x_grids", data=self.CSR_xmesh.reshape(shape))
+            g2.create_dataset("z_grids", data=self.CSR_zmesh.reshape(shape))
+            g2.create_dataset("xkicks", data=self.x_kick.cpu().numpy())
 
     def write_statistics(self):
+        """CSR.py:860-879: step_positions, the reference orbit tables and the statistics dictionary (twiss/...)."""
         if self.rank != 0 or not self.CSR_params.write_wakes:
             return
         path = full_path(self.CSR_params.workdir)
         os.makedirs(path, exist_ok=True)
-        flat = {f"twiss/{k}": v for k, v in self.statistics["twiss"].items()}
-        flat.update({k: v for k, v in self.statistics.items() if k != "twiss"})
-        np.savez(os.path.join(path, f"{self.prefix}-statistics.npz"), step_positions=self.lattice.steps_record,
-                 coords=self.lattice.coords, n_vec=self.lattice.n_vec, tau_vec=self.lattice.tau_vec, **flat)
+        fn = outputs.store_path(os.path.join(path, f"{self.prefix}-statistics"))
+        if os.path.isfile(fn):
+            os.remove(fn)
+        with outputs.open_store(fn, "w") as hf:
+            hf.create_dataset(name="step_positions", data=self.lattice.steps_record, shape=self.lattice.steps_record.shape)
+            hf.create_dataset(name="coords", data=self.lattice.coords)
+            hf.create_dataset(name="n_vec", data=self.lattice.n_vec)
+            hf.create_dataset(name="tau_vec", data=self.lattice.tau_vec)
+            outputs.dict2hdf5(hf, self.statistics)
