@@ -91,8 +91,9 @@ typedef struct dfcsr_history {
     double min_t, min_x, min_z;      /* deposit.py:416-418 (min_x / min_y / min_z there) */
     double delta_t, delta_x, delta_z;/* deposit.py:419-421                               */
     const int32_t* d_row_support;    /* (cap, X, 2) int32 or NULL: per (slot, transverse row) the hull [z_lo, z_hi] of
-                                        the voxels whose density or density gradient is non-zero (z_lo > z_hi: none),
-                                        written by dfcsr_history_row_support.  Every term of the integrand carries a
+                                        the voxels whose density or density gradient is non-zero or whose velocity
+                                        fields are not finite (z_lo > z_hi: none), written by dfcsr_history_regrid
+                                        (or dfcsr_history_row_support).  Every term of the integrand carries a
                                         factor rho or grad rho of the retarded point (CSR.py:732-775), so a sample whose
                                         eight voxels lie outside the hulls contributes exactly 0 and K4 skips it
                                         without touching the history.  NULL = unknown, nothing is skipped.      */

@@ -75,13 +75,20 @@ __device__ __forceinline__ void block_total(double (&v)[NV]) {
 // fixed-order total of a (kStatBlocks, NV) table; result in thread 0 (called by all 256 threads of ONE block)
 template <int NV, int kMaxIdx>
 __device__ __forceinline__ void table_total(const double* table, double (&tot)[NV]) {
+    // all loads first (L2-coherent ld.cg: the rows were written by other CTAs, possibly of other GPUs), then the adds in a
+    // fixed order -- a load-add-load-add chain would serialise 4 NV L2 round trips per thread
+    constexpr int kPer = kStatBlocks / kStatThreads;
+    static_assert(kPer * kStatThreads == kStatBlocks, "table rows must divide evenly among the threads");
+    double p[kPer][NV];
+#pragma unroll
+    for (int i = 0; i < kPer; ++i)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) p[i][k] = __ldcg(table + (size_t)(threadIdx.x + i * kStatThreads) * NV + k);
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-        double s = (k == kMaxIdx) ? 0.0 : 0.0;
-        for (int b = threadIdx.x; b < kStatBlocks; b += kStatThreads) {
-            const double p = ((const volatile double*)table)[(size_t)b * NV + k];
-            s = (k == kMaxIdx) ? absmax_merge(s, p) : s + p;
-        }
+        double s = p[0][k];
+#pragma unroll
+        for (int i = 1; i < kPer; ++i) s = (k == kMaxIdx) ? absmax_merge(s, p[i][k]) : s + p[i][k];
         tot[k] = s;
     }
     block_total<NV, kMaxIdx>(tot);

@@ -175,16 +175,34 @@ __device__ __forceinline__ void cta_total(double (&v)[NV], const bool (&is_max)[
     }
 }
 
-// publish this tile's partials; the last tile to arrive returns true in thread 0 (and may then read all partials)
+// publish this tile's partials; true (in every thread) in the last tile to arrive, which may then read all partials
 __device__ __forceinline__ bool publish_and_ticket(const double* v, int nv, double* partial, int tile, int tiles, unsigned int* ticket) {
-    bool last = false;
+    __shared__ int s_last;
     if (threadIdx.x == 0) {
         for (int k = 0; k < nv; ++k) partial[(size_t)tile * kPartials + k] = v[k];
         __threadfence();
-        last = (atomicAdd(ticket, 1u) == (unsigned)tiles - 1u);
+        const bool last = (atomicAdd(ticket, 1u) == (unsigned)tiles - 1u);
         if (last) { __threadfence(); *ticket = 0u; }
+        s_last = last ? 1 : 0;
     }
-    return last;
+    __syncthreads();
+    return s_last != 0;
+}
+
+// fixed-order total of the tile partials by the whole CTA: thread t takes tiles t, t + 256, ... (loads first, L2-coherent),
+// then the fixed block reduction; result in thread 0
+template <int NV>
+__device__ __forceinline__ void partial_total(const double* partial, int tiles, const bool (&is_max)[NV], double (&tot)[NV]) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) tot[k] = is_max[k] ? -CUDART_INF : 0.0;
+    for (int t = threadIdx.x; t < tiles; t += kDfThreads) {
+        double p[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) p[k] = __ldcg(partial + (size_t)t * kPartials + k);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) tot[k] = is_max[k] ? fmax(tot[k], p[k]) : tot[k] + p[k];
+    }
+    cta_total<NV>(tot, is_max);
 }
 
 struct TileGeom {
@@ -276,12 +294,11 @@ make_df_phase_a(DfParams P) {
     cta_total<2>(v, mx);
     const int tiles = P.tiles_x * P.tiles_z;
     if (publish_and_ticket(v, 2, P.partial, blockIdx.x, tiles, &P.hdr->ticket[0])) {
-        double dsum = 0.0, dmax = -CUDART_INF;
-        for (int t = 0; t < tiles; ++t) {
-            dsum += ((volatile double*)P.partial)[(size_t)t * kPartials + 0];
-            dmax = fmax(dmax, ((volatile double*)P.partial)[(size_t)t * kPartials + 1]);
-        }
-        dmax = dmax / dsum;                              // max of the normalised density
+        double tot[2];
+        partial_total<2>(P.partial, tiles, mx, tot);
+        if (threadIdx.x != 0) return;
+        const double dsum = tot[0];
+        const double dmax = tot[1] / dsum;               // max of the normalised density
         P.scalars[0] = cmax;
         P.scalars[1] = thr;
         P.scalars[2] = dsum;
@@ -370,11 +387,10 @@ make_df_phase_b(DfParams P) {
     const int tiles = P.tiles_x * P.tiles_z;
     double* partial_b = P.partial + (size_t)tiles * kPartials;
     if (publish_and_ticket(v, 4, partial_b, blockIdx.x, tiles, &P.hdr->ticket[1])) {
-        double s_gt = 0.0, n_gt = 0.0, s_eq = 0.0, n_lt = 0.0;
-        for (int t = 0; t < tiles; ++t) {
-            const volatile double* q = (volatile double*)partial_b + (size_t)t * kPartials;
-            s_gt += q[0]; n_gt += q[1]; s_eq += q[2]; n_lt += q[3];
-        }
+        double tot[4];
+        partial_total<4>(partial_b, tiles, mx, tot);
+        if (threadIdx.x != 0) return;
+        const double s_gt = tot[0], n_gt = tot[1], s_eq = tot[2], n_lt = tot[3];
         const double mmean = s_gt / n_gt;                // deposit.py:235
         P.scalars[5] = mmean;
         P.scalars[6] = n_gt;
