@@ -33,7 +33,7 @@
 namespace dfcsr {
 
 constexpr int kTile = 32;         // output tile edge
-constexpr int kDfThreads = 256;
+constexpr int kDfThreads = 512;    // 16 warps: rows of a tile by warp, columns by lane
 constexpr int kMaxWindow = 33;
 constexpr int kPartials = 4;
 
@@ -67,18 +67,23 @@ struct DfParams {
 };
 
 // Savitzky-Golay along one axis for element i of a line of n samples; `at(k)` fetches sample k of the line.
-template <typename Fetch>
-__device__ __forceinline__ double sg_line(const double* taps, const double* edge_lo, const double* edge_hi, int window, int n,
+// kW > 0: compile-time window (fully unrolled taps); kW = 0: runtime window.  Same operations in the same order either way.
+template <int kW, typename Fetch>
+__device__ __forceinline__ double sg_line(const double* taps, const double* edge_lo, const double* edge_hi, int window_rt, int n,
                                           int i, Fetch at) {
+    const int window = kW > 0 ? kW : window_rt;
     const int half = window >> 1;
     double acc = 0.0;
     if (i < half) {
         const double* e = edge_lo + i * window;
+#pragma unroll
         for (int k = 0; k < window; ++k) acc = fma(e[k], at(k), acc);
     } else if (i >= n - half) {
         const double* e = edge_hi + (i - (n - half)) * window;
+#pragma unroll
         for (int k = 0; k < window; ++k) acc = fma(e[k], at(n - window + k), acc);
     } else {
+#pragma unroll
         for (int k = 0; k < window; ++k) acc = fma(taps[k], at(i - half + k), acc);
     }
     return acc;
@@ -231,23 +236,32 @@ __device__ __forceinline__ void load_ops(const DfOps& ops, int window, double* s
 }
 
 // smooth the region `in` (rows r0.., columns c0..; extents rw x cw) along x into `tmp` (tile rows x cw), then along z
-// into out(i, j) for the tile; `emit(i, j, value)` consumes the result
+// into out(i, j) for the tile; `emit(i, j, value)` consumes the result.  Rows go by warp, columns by lane.
+template <int kW, typename Emit>
+__device__ __forceinline__ void smooth_tile_w(const DfParams& P, const TileGeom& g, const double* in, double* tmp,
+                                              const double* s_taps, const double* s_lo, const double* s_hi, Emit emit) {
+    const int nx = P.ax.n, nz = P.az.n, w = P.window;
+    const int th = g.i1 - g.i0 + 1, tw = g.j1 - g.j0 + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kWarps = kDfThreads / 32;
+    for (int ti = warp; ti < th; ti += kWarps)
+        for (int cc = lane; cc < g.cw; cc += 32)
+            tmp[ti * g.cw + cc] = sg_line<kW>(s_taps, s_lo, s_hi, w, nx, g.i0 + ti, [&](int k) { return in[(k - g.r0) * g.cw + cc]; });
+    __syncthreads();
+    for (int ti = warp; ti < th; ti += kWarps)
+        for (int tj = lane; tj < tw; tj += 32) {
+            const double v = sg_line<kW>(s_taps, s_lo, s_hi, w, nz, g.j0 + tj, [&](int k) { return tmp[ti * g.cw + (k - g.c0)]; });
+            emit(g.i0 + ti, g.j0 + tj, v);
+        }
+    __syncthreads();
+}
+
 template <typename Emit>
 __device__ __forceinline__ void smooth_tile(const DfParams& P, const TileGeom& g, const double* in, double* tmp,
                                             const double* s_taps, const double* s_lo, const double* s_hi, Emit emit) {
-    const int nx = P.ax.n, nz = P.az.n, w = P.window;
-    const int th = g.i1 - g.i0 + 1, tw = g.j1 - g.j0 + 1;
-    for (int e = threadIdx.x; e < th * g.cw; e += kDfThreads) {
-        const int ti = e / g.cw, cc = e - ti * g.cw;
-        tmp[e] = sg_line(s_taps, s_lo, s_hi, w, nx, g.i0 + ti, [&](int k) { return in[(k - g.r0) * g.cw + cc]; });
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < th * tw; e += kDfThreads) {
-        const int ti = e / tw, tj = e - ti * tw;
-        const double v = sg_line(s_taps, s_lo, s_hi, w, nz, g.j0 + tj, [&](int k) { return tmp[ti * g.cw + (k - g.c0)]; });
-        emit(g.i0 + ti, g.j0 + tj, v);
-    }
-    __syncthreads();
+    if (P.window == 9) smooth_tile_w<9>(P, g, in, tmp, s_taps, s_lo, s_hi, emit);        // chicane_config.yaml:16
+    else if (P.window == 5) smooth_tile_w<5>(P, g, in, tmp, s_taps, s_lo, s_hi, emit);   // the hard-coded branch, deposit.py:167
+    else smooth_tile_w<0>(P, g, in, tmp, s_taps, s_lo, s_hi, emit);
 }
 
 // max(count) when the deposit did not deliver it
@@ -272,21 +286,28 @@ make_df_phase_a(DfParams P) {
     double* in_c = s_hi + half * P.window;
     double* in_v = in_c + g.rw * g.cw;
     double* tmp = in_v + g.rw * g.cw;
+    double* wx = tmp + kTile * g.cw;            // trapezoid weights of the tile's rows and columns
+    double* wz = wx + kTile;
     load_ops(P.ops, P.window, s_taps, s_lo, s_hi);
+    if (threadIdx.x < kTile) wx[threadIdx.x] = trapz_weight(P.ax, min(g.i0 + (int)threadIdx.x, P.ax.n - 1));
+    else if (threadIdx.x < 2 * kTile) wz[threadIdx.x - kTile] = trapz_weight(P.az, min(g.j0 + (int)threadIdx.x - kTile, nz - 1));
     const double cmax = __longlong_as_double((long long)*P.cmax_bits);
     const double thr = cmax / P.velocity_threshold;
-    for (int e = threadIdx.x; e < g.rw * g.cw; e += kDfThreads) {
-        const int rr = e / g.cw, cc = e - rr * g.cw;
-        const size_t o = (size_t)(g.r0 + rr) * nz + (g.c0 + cc);
-        const double cn = P.count[o], vs = P.vxsum[o];
-        in_c[e] = cn;
-        in_v[e] = (cn > thr) ? vs / cn : vs;            // deposit.py:184
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int rr = warp; rr < g.rw; rr += kDfThreads / 32)
+            for (int cc = lane; cc < g.cw; cc += 32) {
+                const size_t o = (size_t)(g.r0 + rr) * nz + (g.c0 + cc);
+                const double cn = P.count[o], vs = P.vxsum[o];
+                in_c[rr * g.cw + cc] = cn;
+                in_v[rr * g.cw + cc] = (cn > thr) ? vs / cn : vs;            // deposit.py:184
+            }
     }
     __syncthreads();
     double v[2] = {0.0, -CUDART_INF};
     smooth_tile(P, g, in_c, tmp, s_taps, s_lo, s_hi, [&](int i, int j, double d) {
         P.t0[(size_t)i * nz + j] = d;
-        v[0] = fma(trapz_weight(P.ax, i) * trapz_weight(P.az, j), d, v[0]);
+        v[0] = fma(wx[i - g.i0] * wz[j - g.j0], d, v[0]);
         v[1] = fmax(v[1], d);
     });
     smooth_tile(P, g, in_v, tmp, s_taps, s_lo, s_hi, [&](int i, int j, double wv) { P.t1[(size_t)i * nz + j] = wv; });
@@ -340,36 +361,38 @@ make_df_phase_b(DfParams P) {
     double* density_z = P.fields + (size_t)DFCSR_DENSITY_Z * cells;
     double* vx = P.fields + (size_t)DFCSR_VX * cells;
     double* vx_x = P.fields + (size_t)DFCSR_VX_X * cells;
-    for (int e = threadIdx.x; e < erw * ecw; e += kDfThreads) {
-        const int rr = e / ecw, cc = e - rr * ecw;
-        const int i = er0 + rr, j = ec0 + cc;
-        const size_t o = (size_t)i * nz + j;
-        const double d = P.t0[o] / dsum;                 // deposit.py:202
-        const double wv = (d <= thr) ? 0.0 : P.t1[o];    // deposit.py:204 (thr in raw-count units: kept)
-        dn[e] = d;
-        vm[e] = wv;
-        if (i >= g.i0 && i <= g.i1 && j >= g.j0 && j <= g.j1) { density[o] = d; vx[o] = wv; }
-    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kWarps = kDfThreads / 32;
+    for (int rr = warp; rr < erw; rr += kWarps)
+        for (int cc = lane; cc < ecw; cc += 32) {
+            const int i = er0 + rr, j = ec0 + cc;
+            const size_t o = (size_t)i * nz + j;
+            const double d = P.t0[o] / dsum;                 // deposit.py:202
+            const double wv = (d <= thr) ? 0.0 : P.t1[o];    // deposit.py:204 (thr in raw-count units: kept)
+            dn[rr * ecw + cc] = d;
+            vm[rr * ecw + cc] = wv;
+            if (i >= g.i0 && i <= g.i1 && j >= g.j0 && j <= g.j1) { density[o] = d; vx[o] = wv; }
+        }
     __syncthreads();
     double v[4] = {0.0, 0.0, 0.0, 0.0};        // sum / count of vx_x where density > thr2; sum where == thr2; count where <
     for (int f = 0; f < 3; ++f) {
         // gradient field f on the smoothing region: d(density)/dx, d(density)/dz, d(vx)/dx   (deposit.py:212-213)
-        for (int e = threadIdx.x; e < g.rw * g.cw; e += kDfThreads) {
-            const int rr = e / g.cw, cc = e - rr * g.cw;
-            const int i = g.r0 + rr, j = g.c0 + cc;
-            const double* src = (f == 2) ? vm : dn;
-            double gv;
-            if (f == 1) {
-                const GradCoef c = gcz[cc];
-                const double* row = src + (i - er0) * ecw - ec0;
-                gv = grad_apply(c, row[c.lo], row[j], row[c.hi]);
-            } else {
-                const GradCoef c = gcx[rr];
-                const double* col = src + (j - ec0) - er0 * ecw;
-                gv = grad_apply(c, col[c.lo * ecw], col[i * ecw], col[c.hi * ecw]);
+        for (int rr = warp; rr < g.rw; rr += kWarps)
+            for (int cc = lane; cc < g.cw; cc += 32) {
+                const int i = g.r0 + rr, j = g.c0 + cc;
+                const double* src = (f == 2) ? vm : dn;
+                double gv;
+                if (f == 1) {
+                    const GradCoef c = gcz[cc];
+                    const double* row = src + (i - er0) * ecw - ec0;
+                    gv = grad_apply(c, row[c.lo], row[j], row[c.hi]);
+                } else {
+                    const GradCoef c = gcx[rr];
+                    const double* col = src + (j - ec0) - er0 * ecw;
+                    gv = grad_apply(c, col[c.lo * ecw], col[i * ecw], col[c.hi * ecw]);
+                }
+                grad[rr * g.cw + cc] = gv;
             }
-            grad[e] = gv;
-        }
         __syncthreads();
         double* out = (f == 0) ? density_x : ((f == 1) ? density_z : vx_x);
         smooth_tile(P, g, grad, tmp, s_taps, s_lo, s_hi, [&](int i, int j, double sv) {
@@ -471,7 +494,7 @@ extern "C" int dfcsr_make_df(const double* d_count, const double* d_vxsum, dfcsr
     const int half = window >> 1;
     const int reg = kTile + 2 * half;                  // largest smoothing-region edge
     const size_t ops_words = kMaxWindow + 2 * (size_t)half * window;
-    const size_t smem_a = (ops_words + 2 * (size_t)reg * reg + (size_t)kTile * reg) * sizeof(double);
+    const size_t smem_a = (ops_words + 2 * (size_t)reg * reg + (size_t)kTile * reg + 2 * kTile) * sizeof(double);
     const size_t smem_b = (ops_words + 2 * (size_t)(reg + 2) * (reg + 2) + (size_t)reg * reg + (size_t)kTile * reg) * sizeof(double) +
                           2 * (size_t)reg * sizeof(GradCoef);
     // opt in to more than 48 KB of dynamic shared memory only when a window needs it, and only once per size (the call
