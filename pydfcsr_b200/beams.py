@@ -173,21 +173,31 @@ class Beam:
         """x with the x-z chirp removed (beams.py:206-211); a device tensor."""
         return self.x - (self._slope[0] * self.z + self._slope[1])
 
+    def twiss_async(self):
+        """Enqueue the covariance pass behind the Twiss statistics; returns a callable that waits for it (once) and
+        returns the dictionary of `twiss`.  Lets the driver collect per-step statistics without a host sync per step."""
+        pending = ops.beam_cov_async(self.coords, centre=self._centre6, shards=self.shards)
+        energy = self._init_energy
+
+        def resolve():
+            _, cov6 = pending.get()
+            out = {}
+            for plane, idx in (("x", (0, 1, 5)), ("y", (2, 3, 5))):
+                cov = cov6[np.ix_(idx, idx)]
+                d2, xd, pd = cov[2, 2], cov[0, 2], cov[1, 2]
+                eb, eg, ea = cov[0, 0] - xd ** 2 / d2, cov[1, 1] - pd ** 2 / d2, -cov[0, 1] + xd * pd / d2
+                emit = np.sqrt(eb * eg - ea ** 2)
+                vals = dict(alpha=ea / emit, beta=eb / emit, gamma=eg / emit, emit=emit, eta=xd / d2, etap=pd / d2,
+                            norm_emit=emit * energy / MC2)
+                out.update({f"{k}_{plane}": v for k, v in vals.items()})
+            return out
+        return resolve
+
     @property
     def twiss(self):
         """Twiss/dispersion from the 3x3 covariances of (x, px, pz) and (y, py, pz) (twiss.py:2-71); the 6x6
         covariance comes from one device reduction (ops.beam_cov)."""
-        _, cov6 = ops.beam_cov(self.coords, centre=self._centre6, shards=self.shards)
-        out = {}
-        for plane, idx in (("x", (0, 1, 5)), ("y", (2, 3, 5))):
-            cov = cov6[np.ix_(idx, idx)]
-            d2, xd, pd = cov[2, 2], cov[0, 2], cov[1, 2]
-            eb, eg, ea = cov[0, 0] - xd ** 2 / d2, cov[1, 1] - pd ** 2 / d2, -cov[0, 1] + xd * pd / d2
-            emit = np.sqrt(eb * eg - ea ** 2)
-            vals = dict(alpha=ea / emit, beta=eb / emit, gamma=eg / emit, emit=emit, eta=xd / d2, etap=pd / d2,
-                        norm_emit=emit * self._init_energy / MC2)
-            out.update({f"{k}_{plane}": v for k, v in vals.items()})
-        return out
+        return self.twiss_async()()
 
     def to_host(self) -> np.ndarray:
         """(6, n_total) host array of ALL particles (collective when the particles are sharded)."""

@@ -117,26 +117,34 @@ class CSR2D:
                            "slope": np.zeros((n, 2))}
         for k in ("sigma_x", "sigma_z", "sigma_energy", "mean_x", "mean_z", "mean_energy"):
             self.statistics[k] = np.zeros(n)
+        self._pending_twiss = []
         self.update_statistics(step=0)
         self.inbend = False
         self.afterbend = False
         self.R_rec = None
         self.phi_rec = None
 
+    def _flush_statistics(self):
+        e0 = self.beam.init_energy
+        for step, resolve, pending in self._pending_twiss:
+            for k, v in resolve().items():
+                self.statistics["twiss"][k][step] = v
+            st = pending.get()                       # the statistics pass that was current when the step was recorded
+            self.statistics["slope"][step, :] = (st[_lib.S_SLOPE], st[_lib.S_INTERCEPT])
+            self.statistics["sigma_x"][step] = st[_lib.S_SIGMA_X]
+            self.statistics["sigma_z"][step] = st[_lib.S_SIGMA_Z]
+            self.statistics["sigma_energy"][step] = st[_lib.S_SIGMA_PZ] * e0
+            self.statistics["mean_x"][step] = st[_lib.S_MEAN_X]
+            self.statistics["mean_z"][step] = st[_lib.S_MEAN_Z]
+            self.statistics["mean_energy"][step] = (st[_lib.S_MEAN_PZ] + 1) * e0
+        self._pending_twiss = []
+
     def update_statistics(self, step):
         if step >= self.lattice.total_steps:
             return
-        tw = self.beam.twiss
-        for k, v in tw.items():
-            self.statistics["twiss"][k][step] = v
-        b = self.beam
-        self.statistics["slope"][step, :] = b._slope
-        self.statistics["sigma_x"][step] = b._sigma_x
-        self.statistics["sigma_z"][step] = b._sigma_z
-        self.statistics["sigma_energy"][step] = b.sigma_energy
-        self.statistics["mean_x"][step] = b._mean_x
-        self.statistics["mean_z"][step] = b._mean_z
-        self.statistics["mean_energy"][step] = b.mean_energy
+        # the covariance pass is only enqueued; its 27 numbers are collected by _flush_statistics (end of run(), or
+        # when the statistics are written), so that a lattice step does not pay a host synchronisation for them
+        self._pending_twiss.append((step, self.beam.twiss_async(), self.beam._pending_stats))
 
     # ------------------------------------------------------------------------------- multi-GPU
     def init_MPI(self):
@@ -267,9 +275,11 @@ class CSR2D:
                 self._log("Finish step {}, s = {},  in {} seconds".format(step_count, b.position, time.time() - t0))
                 step_count += 1
                 if stop_time and b.position > stop_time:
+                    self._flush_statistics()
                     return
             ele_prev = ele
             ele_count += 1
+        self._flush_statistics()
         self.dump_beam(label="end")
         self.write_statistics()
 
@@ -434,6 +444,7 @@ class CSR2D:
 
     def write_statistics(self):
         """CSR.py:860-879: step_positions, the reference orbit tables and the statistics dictionary (twiss/...)."""
+        self._flush_statistics()
         if self.rank != 0 or not self.CSR_params.write_wakes:
             return
         path = full_path(self.CSR_params.workdir)

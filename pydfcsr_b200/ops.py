@@ -141,14 +141,42 @@ def beam_stats(x: torch.Tensor, z: torch.Tensor, pz: torch.Tensor | None = None,
 _cov_ws: dict = {}
 
 
-def beam_cov(coords, centre=None, shards=None) -> tuple[np.ndarray, np.ndarray]:
-    """(means[6], cov[6, 6]) of the six coordinate tensors (x, px, y, py, z, pz); np.cov normalisation (ddof = 1).
-    One device pass + 27 doubles to the host.  Synchronises.  centre / shards: as for beam_stats_async."""
+class PendingCov:
+    """Result of an asynchronous covariance pass: `get()` waits for the device (once) and returns (means[6], cov[6, 6])."""
+
+    def __init__(self, host_buf, event, free_list):
+        self._buf, self._event, self._value, self._free = host_buf, event, None, free_list
+
+    def get(self):
+        if self._value is None:
+            self._event.synchronize()
+            flat = self._buf.numpy().copy()
+            self._free.append(self._buf)
+            self._buf = None
+            cov = np.zeros((6, 6))
+            cov[np.triu_indices(6)] = flat[6:]
+            cov = cov + np.triu(cov, 1).T
+            self._value = (flat[:6].copy(), cov)
+        return self._value
+
+    def __del__(self):
+        try:
+            if self._buf is not None:
+                self._event.synchronize()
+                self._free.append(self._buf)
+        except Exception:
+            pass
+
+
+def beam_cov_async(coords, centre=None, shards=None) -> PendingCov:
+    """Enqueue the covariance pass over the six coordinate tensors (x, px, y, py, z, pz); np.cov normalisation (ddof = 1).
+    One device pass + 27 doubles mirrored to pinned host memory; nothing blocks.  centre / shards: as for beam_stats_async."""
     dev = coords[0].device
     if dev not in _cov_ws:
-        _cov_ws[dev] = (torch.zeros(lib.dfcsr_beam_cov_workspace(), dtype=torch.uint8, device=dev),
-                        torch.zeros(27, dtype=F64, device=dev), torch.zeros(27, dtype=F64).pin_memory())
-    ws, d_out, h_out = _cov_ws[dev]
+        _cov_ws[dev] = [torch.zeros(lib.dfcsr_beam_cov_workspace(), dtype=torch.uint8, device=dev), []]
+    ws, free = _cov_ws[dev]
+    host = free.pop() if free else torch.zeros(27, dtype=F64).pin_memory()
+    d_out = torch.empty(27, dtype=F64, device=dev)
     ptrs = [_ptr(_f64(c, "coords")) for c in coords]
     ctr = _centre(centre, 6)
     if shards is None:
@@ -160,13 +188,19 @@ def beam_cov(coords, centre=None, shards=None) -> tuple[np.ndarray, np.ndarray]:
               "dfcsr_beam_cov_partial")
         shards.exchange(table)
         check(lib.dfcsr_beam_cov_final(_ptr(table), shards.n_total, ctr, _ptr(d_out), _stream()), "dfcsr_beam_cov_final")
-    h_out.copy_(d_out, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
-    flat = h_out.numpy()
-    cov = np.zeros((6, 6))
-    cov[np.triu_indices(6)] = flat[6:]
-    cov = cov + np.triu(cov, 1).T
-    return flat[:6].copy(), cov
+    global _mirror_ok
+    if _mirror_ok:
+        _mirror_ok = lib.dfcsr_mirror_to_host(_ptr(d_out), C.c_void_p(host.data_ptr()), 27, _stream()) == 0
+    if not _mirror_ok:
+        host.copy_(d_out, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    return PendingCov(host, ev, free)
+
+
+def beam_cov(coords, centre=None, shards=None) -> tuple[np.ndarray, np.ndarray]:
+    """(means[6], cov[6, 6]); synchronises.  See beam_cov_async."""
+    return beam_cov_async(coords, centre, shards).get()
 
 
 # ---------------------------------------------------------------------------------------------
