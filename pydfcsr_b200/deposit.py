@@ -69,7 +69,9 @@ class DF_tracker:
         self.z_grid_interp = None
         self._x_axis_interp = None
         self._z_axis_interp = None
-        self._ring = None              # (cap, X, Z, 6) device tensor
+        self._ring = None              # (cap, X, Z, 6) device tensor (a view of _ring_storage)
+        self._ring_storage = None
+        self._support_storage = None
         self._support = None           # (cap, X, 2) int32 row hulls of the non-zero density voxels, slot-aligned with the ring
         self._head = 0
         self.history: ops.DeviceHistory | None = None
@@ -212,9 +214,22 @@ class DF_tracker:
         ring = self._ring
         if ring is None or ring.shape[1] != X or ring.shape[2] != Z or ring.shape[0] < need:
             cap = self._capacity_for(need)
-            self._ring = None          # release the old ring before allocating the new one
-            self._ring = ops.new_slices((cap, X, Z), self.precision, self.device)
-            self._support = ops.new_row_support(cap, X, self.device)
+            # A rebuild changes the slice shape almost every time (29 rebuilds in the 133 steps of the bundled chicane), and
+            # a fresh device allocation of up to several GB costs about a millisecond each way: the ring is a VIEW of one
+            # storage block that only ever grows.
+            elems = _lib.VOXEL_DOUBLES if self.precision == "fp64" else _lib.VOXEL_FLOATS
+            words = cap * X * Z * elems
+            if self._ring_storage is None or self._ring_storage.numel() < words:
+                self._ring = None      # release the old block before allocating the new one
+                self._ring_storage = None
+                self._ring_storage = ops.new_slices((words // elems + 1,), self.precision, self.device).view(-1)
+            self._ring = self._ring_storage[:words].view(cap, X, Z, elems)
+            sup_words = cap * X * 2
+            if self._support_storage is None or self._support_storage.numel() < sup_words:
+                self._support_storage = torch.empty(sup_words + 2 * X, dtype=torch.int32, device=self.device)
+            self._support = self._support_storage[:sup_words].view(cap, X, 2)
+            self._support[..., 0] = torch.iinfo(torch.int32).max
+            self._support[..., 1] = -1
             self._head = 0
             return True
         return False
@@ -232,8 +247,12 @@ class DF_tracker:
         old, T = self._ring, len(self.time_interp) - 1
         cap_old = old.shape[0]
         cap = self._capacity_for(T + 1 + max(4, T // 4))
-        new = torch.empty((cap,) + tuple(old.shape[1:]), dtype=old.dtype, device=self.device)
-        sup = ops.new_row_support(cap, old.shape[1], self.device)
+        storage = torch.empty(cap * old[0].numel() + old[0].numel(), dtype=old.dtype, device=self.device)
+        new = storage[:cap * old[0].numel()].view((cap,) + tuple(old.shape[1:]))
+        sup_storage = torch.empty(cap * old.shape[1] * 2 + 2 * old.shape[1], dtype=torch.int32, device=self.device)
+        sup = sup_storage[:cap * old.shape[1] * 2].view(cap, old.shape[1], 2)
+        sup[..., 0] = torch.iinfo(torch.int32).max
+        sup[..., 1] = -1
         first = min(T, cap_old - self._head)                 # slices from head to the end of the old ring
         new[:first].copy_(old[self._head:self._head + first])
         sup[:first].copy_(self._support[self._head:self._head + first])
@@ -241,6 +260,7 @@ class DF_tracker:
             new[first:T].copy_(old[:T - first])
             sup[first:T].copy_(self._support[:T - first])
         self._ring, self._support, self._head = new, sup, 0
+        self._ring_storage, self._support_storage = storage, sup_storage
 
     def _regrid(self, rec: _Record, idx):
         """Re-grid one logged record into ring slot `idx` and refresh that slot's row support."""
