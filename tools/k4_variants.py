@@ -2,8 +2,8 @@
 tools/build_dev.py) on the bench workload in ONE process and compare each variant's wake grids with the first one.
 
     python tools/build_dev.py && DFCSR_LIB=pydfcsr_b200/libdfcsr_b200_dev.so python tools/k4_variants.py [reps] [cfg ...]
-    DFCSR_TILT=2.5 adds an x-z tilt (chirp-band quadrature); cfg 0 = shipped default, 50 = direct-gather kernel,
-    60 = patch kernel with the patch disabled, 61.. = patch of 8, 16, ... nodes per warp
+    DFCSR_TILT=2.5 adds an x-z tilt (chirp-band quadrature); cfg 0 = shipped kernel, 20 / 40 = without bracket and queue interleave,
+    30 = register cache, 25 = two x' nodes per lane, 70 = patch kernel (71.. = patch of 0, 8, 16, ... nodes per warp), 80 = lean node records
 """
 import os
 import sys
@@ -17,7 +17,7 @@ import bench  # noqa: E402
 from pydfcsr_b200 import CSR2D  # noqa: E402
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-cfgs = [int(a) for a in sys.argv[2:]] or [50, 0, 60, 64, 68, 72, 78]
+cfgs = [int(a) for a in sys.argv[2:]] or [0, 20, 40, 30, 25, 70, 73, 80]
 wl = bench.WORKLOAD
 inp = bench._input_dict(wl)
 tilt = os.environ.get("DFCSR_TILT")
