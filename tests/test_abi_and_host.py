@@ -118,6 +118,27 @@ for n in (7, 10, 4096):
     assert np.array_equal(got, full), (rank, n)
 # the fused K4 exchange needs NCCL ranks with CUDA peer mappings: on gloo/CPU the collective decision is "NCCL path"
 assert D.make_peer_wake_grid(4096, torch.device("cpu")) is None
+# particle shards (host logic; the kernels are covered on the GPU): whole chunks per rank, exact cover, gather restores
+# the bunch, and the table exchange of the NCCL/gloo fallback completes every rank's table
+for n in (10_003, 1_000_000, 1500):
+    sh = D.ParticleShards(n, torch.device("cpu"), max_cells=64, use_peers=False)
+    assert sh.mode == "nccl" and sh.chunk == -(-n // 1024)
+    ranges = [None] * world
+    dist.all_gather_object(ranges, (sh.lo, sh.hi, sh.first_block, sh.n_blocks))
+    assert ranges[0][0] == 0 and ranges[-1][1] == n and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    assert sum(r[3] for r in ranges) == 1024 and all(r[0] == min(r[2] * sh.chunk, n) for r in ranges)
+    full = torch.arange(n, dtype=torch.float64)
+    assert torch.equal(sh.gather(sh.local_slice(full).clone()), full)
+    table, ptrs = sh.stats_table(0)
+    assert ptrs is None and float(table.abs().sum()) == 0.0
+    table.view(1024, 8)[sh.first_block:sh.first_block + sh.n_blocks] = float(rank + 1)
+    sh.exchange(table)
+    want = torch.cat([torch.full((r[3], 8), float(k + 1), dtype=torch.float64) for k, r in enumerate(ranges)])
+    assert torch.equal(table.view(1024, 8), want)
+    q, qptr = sh.q_buffer(64)
+    q.fill_(rank + 1)
+    sh.reduce_q(q)
+    assert int(q[0]) == sum(range(1, world + 1)) and len(qptr) == 1
 dist.barrier()
 open(os.path.join(sys.argv[2], f"ok{rank}"), "w").write("ok")     # one file per rank: stdout of two ranks interleaves
 '''
