@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DFCSR_ABI_VERSION 3
+#define DFCSR_ABI_VERSION 4
 #define DFCSR_VOXEL_DOUBLES 6   /* fp64 voxel: 48 bytes */
 #define DFCSR_VOXEL_FLOATS 8    /* fp32 voxel: 32 bytes {density, density_x, density_z, vx, vx_x, 0, 0, 0} */
 #define DFCSR_LATTICE_DOUBLES 6
@@ -287,6 +287,39 @@ int dfcsr_wake_grid_peers(const dfcsr_history* hist, const dfcsr_lattice* lat, c
                           dfcsr_axis x_axis, dfcsr_axis z_axis, double slope, double intercept,
                           int64_t first, int64_t count, int64_t stride, const uint64_t* h_peer_grids, int32_t n_peers,
                           unsigned long long* d_counters, void* stream);
+
+/* ---- K4, x-group mapping (csrc/wake_xgroup.cuh): same get_CSR_wake results (CSR.py:454-602), other work split ------
+ * Without chirp band (|slope0| <= 1, CSR.py:480) the (x', s') quadrature nodes of an observation point depend on its s
+ * only, and the mesh of get_CSR_mesh is a tensor grid (CSR.py:380-389): all points of one z row share their nodes.  A
+ * GROUP is up to 32 mesh points with the same z index and consecutive x indices (global group g = iz * ceil(nx/32) + gx);
+ * the kernel gives every point of a group one warp lane, walks the s' nodes in sequence and keeps the transverse-blended
+ * corners of each lane's history cell in registers, so most samples need no history load at all (1.3-1.5x faster than
+ * the point kernel on a bunch that fills its grid).  The summation order differs from dfcsr_wake_grid (results agree to
+ * ~1e-15 relative, both within 1e-10 of the reference) and is a function of the plan only: any split of the groups over
+ * launches / ranks gives bitwise the same grid.
+ * dfcsr_wake_xgroup_plan: n_groups = 0 when the mapping does not apply to this step (chirp band, a sparse grid that
+ * dfcsr_wake_uses_skipping would serve, fewer than 70 % of the lanes carrying a point, integration zbins too large);
+ * the plan depends on the history geometry, the beam scalars and the WHOLE mesh, never on the split. */
+typedef struct dfcsr_xgroup_plan {
+    int64_t n_groups;                  /* groups of the whole mesh; 0 = use dfcsr_wake_grid                     */
+    int32_t unit_nodes;                /* x' nodes per partial sum (fixes the summation order)                  */
+    int32_t max_units;                 /* partial sums per group                                                */
+    int64_t workspace_bytes_per_group; /* d_workspace of a launch must hold group_count times this              */
+} dfcsr_xgroup_plan;
+
+int dfcsr_wake_xgroup_plan(const dfcsr_history* hist, const dfcsr_wake_params* wp, dfcsr_axis x_axis, dfcsr_axis z_axis,
+                           dfcsr_xgroup_plan* plan);
+
+/* Groups group_first + k * group_stride, k in [0, group_count).  d_dE / d_kick are FULL (x_axis.n * z_axis.n) arrays
+ * indexed by mesh point (only the points of the launched groups are written; may be NULL when peers are given);
+ * h_peer_grids / n_peers as in dfcsr_wake_grid_peers (NULL / 0: none).  d_workspace: caller-owned scratch (queue
+ * counters, cleared by the launch, and partial sums); it must not be shared by launches that may run concurrently.
+ * d_counters as in dfcsr_wake_mesh. */
+int dfcsr_wake_grid_xgroups(const dfcsr_history* hist, const dfcsr_lattice* lat, const dfcsr_wake_params* wp,
+                            dfcsr_axis x_axis, dfcsr_axis z_axis, double slope, double intercept,
+                            int64_t group_first, int64_t group_count, int64_t group_stride, double* d_dE, double* d_kick,
+                            const uint64_t* h_peer_grids, int32_t n_peers, void* d_workspace, int64_t workspace_bytes,
+                            unsigned long long* d_counters, void* stream);
 
 /* 1 if the wake launches above would use zero-density skipping for this history and these beam scalars (row-support
  * table present and the grid sparse by construction: |slope0| > 1, the chirp-band branch of CSR.py:480, or a history

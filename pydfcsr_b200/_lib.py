@@ -17,7 +17,7 @@ VOXEL_F64, VOXEL_F32 = 0, 1
 LATTICE_DOUBLES = 6
 STATS_DOUBLES = 16
 DF_SCALARS = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_PEERS = 8
 SKIP_MODES = {"auto": 0, "on": 1, "off": 2}
 
@@ -60,6 +60,11 @@ class WakeParams(C.Structure):
                 ("nx", C.c_int32), ("nz", C.c_int32), ("skip_mode", C.c_int32), ("reserved", C.c_int32)]
 
 
+class XGroupPlan(C.Structure):
+    _fields_ = [("n_groups", C.c_int64), ("unit_nodes", C.c_int32), ("max_units", C.c_int32),
+                ("workspace_bytes_per_group", C.c_int64)]
+
+
 _P = C.c_void_p
 _D = C.c_double
 _I = C.c_int32
@@ -98,6 +103,9 @@ SIGNATURES = {
                                   _L, _L, _P, _P, _P, _P]),
     "dfcsr_wake_grid_peers": (C.c_int, [C.POINTER(History), C.POINTER(Lattice), C.POINTER(WakeParams), Axis, Axis, _D, _D,
                                         _L, _L, _L, C.POINTER(C.c_uint64), _I, _P, _P]),
+    "dfcsr_wake_xgroup_plan": (C.c_int, [C.POINTER(History), C.POINTER(WakeParams), Axis, Axis, C.POINTER(XGroupPlan)]),
+    "dfcsr_wake_grid_xgroups": (C.c_int, [C.POINTER(History), C.POINTER(Lattice), C.POINTER(WakeParams), Axis, Axis, _D, _D,
+                                          _L, _L, _L, _P, _P, C.POINTER(C.c_uint64), _I, _P, _L, _P, _P]),
     "dfcsr_wake_uses_skipping": (C.c_int, [C.POINTER(History), C.POINTER(WakeParams)]),
     "dfcsr_wake_point_debug": (C.c_int, [C.POINTER(History), C.POINTER(Lattice), C.POINTER(WakeParams),
                                          _D, _D, _P, _P, _L, _P, _P, _P]),

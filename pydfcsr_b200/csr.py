@@ -54,6 +54,11 @@ class CSR2D:
         # CSR.py:121-125, whose cost differs from rank to rank with the number of in-grid samples).  Same grid bits either
         # way; the NCCL all-gather path always uses the reference's blocks.
         self.mesh_split = os.environ.get("DFCSR_MESH_SPLIT", "interleaved")
+        # which work split the wake kernel uses: "auto" = one lane per observation point (x-groups, ops.wake_grid_xgroups)
+        # whenever its plan applies to the step -- no chirp band, a bunch that fills its history grid, a mesh row of
+        # >= 23 points -- else one CTA per point (ops.wake_grid); "point" forces the latter.  The plan depends on the step's
+        # scalars and the whole mesh only, so every rank of a parallel run takes the same decision.
+        self.wake_mapping = os.environ.get("DFCSR_WAKE_MAPPING", "auto")
         self.timestamp = isotime()
         self.verbose = verbose
         self.parallel = bool(parallel)
@@ -326,14 +331,29 @@ class CSR2D:
                                mean_x=b._mean_x, formation_window=ip.n_formation_length * self.formation_length,
                                csr_scaling=self.CSR_scaling, nx=ip.xbins, nz=ip.zbins, skip=getattr(self, "skip_mode", "auto"))
 
+    def _xgroup_plan(self, wp):
+        """The x-group plan of this step, or None when the point kernel serves it (dfcsr_wake_xgroup_plan)."""
+        if self.wake_mapping == "point":
+            return None
+        xa, za = self._mesh_axes
+        plan = ops.wake_xgroup_plan(self.DF_tracker.history, wp, xa, za)
+        self.last_wake_mapping = "xgroup" if plan.n_groups > 0 else "point"
+        return plan if plan.n_groups > 0 else None
+
     def calculate_2D_CSR(self):
         """CSR.py:397-418: the whole mesh in one launch; results stay on the device
         (`dE_dct`, `x_kick` are (xbins, zbins) CUDA tensors; `.cpu().numpy()` for host copies)."""
         p = self.CSR_params
         lat = self.lattice.device_tables(self.device)
         xa, za = self._mesh_axes
-        de, kick = ops.wake_grid(self.DF_tracker.history, lat, self._wake_params(), xa, za, *self._mesh_slope,
-                                 counters=getattr(self, "wake_counters", None))
+        wp = self._wake_params()
+        plan = self._xgroup_plan(wp)
+        if plan is not None:
+            de, kick = ops.wake_grid_xgroups(self.DF_tracker.history, lat, wp, xa, za, *self._mesh_slope, plan=plan,
+                                             counters=getattr(self, "wake_counters", None))
+        else:
+            de, kick = ops.wake_grid(self.DF_tracker.history, lat, wp, xa, za, *self._mesh_slope,
+                                     counters=getattr(self, "wake_counters", None))
         self.dE_dct = de.reshape(p.xbins, p.zbins)
         self.x_kick = kick.reshape(p.xbins, p.zbins)
 
@@ -346,6 +366,32 @@ class CSR2D:
         lat = self.lattice.device_tables(self.device)
         xa, za = self._mesh_axes
         peer = getattr(self, "_peer_grid", None)
+        wp = self._wake_params()
+        plan = self._xgroup_plan(wp)
+        if plan is not None:
+            # groups rank, rank + P, ... of the x-group mapping (every rank derives the same plan; the grid bits do not
+            # depend on the split).  With peer memory the kernel stores into all ranks' grids; otherwise every rank fills
+            # its groups of a full grid and ONE all-gather + a per-point selection of the owning rank assembles them.
+            if peer is not None:
+                grid, ptrs, handle = peer.next()
+                ops.wake_grid_xgroups(self.DF_tracker.history, lat, wp, xa, za, *self._mesh_slope, plan=plan,
+                                      group_first=self.rank, group_stride=self.world_size, peer_ptrs=ptrs,
+                                      counters=getattr(self, "wake_counters", None))
+                handle.barrier(channel=0)
+                full = grid.clone()
+            else:
+                mine = torch.zeros((2, n), dtype=torch.float64, device=self.device)
+                ops.wake_grid_xgroups(self.DF_tracker.history, lat, wp, xa, za, *self._mesh_slope, plan=plan,
+                                      group_first=self.rank, group_stride=self.world_size, out=mine,
+                                      counters=getattr(self, "wake_counters", None))
+                key = (p.xbins, p.zbins)
+                if getattr(self, "_xgroup_owner_key", None) != key:
+                    self._xgroup_owner = dist_utils.xgroup_owner(p.xbins, p.zbins, self.world_size, self.device)
+                    self._xgroup_owner_key = key
+                full = dist_utils.all_gather_select(mine, self._xgroup_owner)
+            self.dE_dct = full[0].reshape(p.xbins, p.zbins)
+            self.x_kick = full[1].reshape(p.xbins, p.zbins)
+            return
         if peer is not None:
             grid, ptrs, handle = peer.next()
             if self.mesh_split == "interleaved":      # points rank, rank + P, ...: equal work on every rank
@@ -354,7 +400,7 @@ class CSR2D:
             else:                                     # the reference's contiguous blocks (CSR.py:121-125)
                 first, stride, count = int(self.displ[self.rank]), 1, int(self.count[self.rank])
             try:
-                ops.wake_grid_peers(self.DF_tracker.history, lat, self._wake_params(), xa, za, *self._mesh_slope,
+                ops.wake_grid_peers(self.DF_tracker.history, lat, wp, xa, za, *self._mesh_slope,
                                     first=first, count=count, stride=stride, peer_ptrs=ptrs,
                                     counters=getattr(self, "wake_counters", None))
             except _lib.DfcsrError as e:

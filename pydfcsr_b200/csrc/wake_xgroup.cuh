@@ -1,0 +1,358 @@
+// wake_xgroup.cuh — K4, second mapping: one warp lane per OBSERVATION point, 32 observation points that share s.
+// Included by wake.cu (uses its device helpers); same reference lines: CSR.py:397-451, 454-602, 605-782,
+// interp3D.py:18-66, interp1D.py:13-36.
+//
+// Why a second mapping.  Without chirp band (|slope| <= 1, CSR.py:480) the quadrature nodes of an observation point
+// (s, x) depend on s only: x' nodes are centred on x0 = (s - t) tan(theta) and s' nodes on s (CSR.py:482-520).  The
+// mesh get_CSR_mesh builds is a tensor grid (CSR.py:380-389), so all observation points of one z row share their
+// (x', s') nodes, and tools/k4_sample_stats.py shows (bench workload) that the SAME sample of neighbouring observation
+// points falls into the same (t', z) history cell in 98 % (far rectangles) / 71 % (near rectangle) of the cases, and
+// that along s' a sample's cell moves by 0.001 (middle rectangle) to 0.09 (far rectangle) z cells per node.  The
+// point-per-CTA kernel (lane = s' node) cannot use either fact: every lane fetches 8 voxels x 40 B for every sample,
+// and the L1 -> register path (320 B per lane-sample) is its binding unit (profiles/k4_r2_bench.txt).
+//
+// Mapping here: a GROUP = up to 32 mesh points with the same z index and consecutive x indices; lane = point.  A warp
+// walks one x' node through the s' nodes IN SEQUENCE.  Per step all lanes share the node record (one broadcast read),
+// the history rows and the transverse fraction; each lane keeps the four transverse-blended (t', z) corners of its
+// current cell in registers (20 doubles) and reloads them only when ITS cell changes: in the middle rectangle that is
+// about once per x' node, in the far rectangle every ~11 nodes; ahead of the observer (z_ret moves 2-7 cells per node)
+// every step, which costs what the direct gather costs.  A hit needs no history load at all and a 4-corner blend.
+//
+// Work split and summation order (bitwise independent of the launch geometry and of the rank split):
+//   * the pruned x' nodes of all rectangles form one list; UNIT u = nodes [u U, (u+1) U) of it; a warp accumulates a
+//     unit per lane in node order, s' order, and stores the unit's 2 x 32 sums to the group's partial table;
+//   * the warps of all CTAs that serve a group (any number) draw units from the group's queue (a global counter), most
+//     expensive rectangle first; which warp computes a unit does not matter, its sums land in the unit's slot;
+//   * every finished unit is counted; the warp that finishes the group's LAST unit adds the unit sums in unit order and
+//     writes the 32 points (to the local arrays and/or, over NVLink, to every rank's grid).  No CTA-wide barrier after
+//     set-up: a warp that finds the queue empty just exits.
+// U depends on the global mesh and the integration parameters only (xgroup_plan), never on the split.
+#pragma once
+// (included INSIDE namespace dfcsr of wake.cu, after the shared device helpers)
+
+constexpr int kXRec = 10;          // base_x, base_y, n'x, n'y, tau'x, tau'y, kappa, s', w_s, pad: 80 B, five LDS.128
+constexpr int kXThreads = 256;
+constexpr int kXWarps = kXThreads / 32;
+
+struct XGroupShared {
+    Region reg[kMaxRegions];
+    double X0, Y0, nx, ny, tx, ty;   // orbit, normal, tangent at s (shared by the group)
+    double s, x_mid, x_half;         // group's s; centre and half width of its x values (s' bracket)
+    int nreg;
+    int jlo[kMaxRegions], jhi[kMaxRegions];
+    int node_base[kMaxRegions + 1];  // prefix of pruned x' nodes per rectangle
+    int skip;                        // 1: the group's queue was already empty when this CTA arrived
+};
+
+struct XGroupArgs {
+    long long group_first, group_stride;   // group k of the launch is global group group_first + k * group_stride
+    int ngroups;                           // groups of this launch (the grid is ngroups x CTAs-per-group)
+    int unit_nodes;                        // U
+    int max_units;                         // rows of a group's partial table
+    double* partials;                      // [groups of the launch][max_units][64]
+    unsigned int* tickets;                 // [groups of the launch][2] = {units handed out, units finished}; zeroed by the launcher
+};
+
+// the s'-only constants of every node of every rectangle as 80-byte records with base = R0(s) - R0(s') instead of the
+// point's C = base + x n(s) (CSR.py:645: the lanes add their own x n(s)), and the bracket of the s' nodes that can reach
+// the history grid for ANY x' of the pruned range and ANY x of the group: r(x, x') = |base + x n - x' n'| differs from
+// r(x_mid, x') by at most |x - x_mid| |n| (triangle inequality), so the point-kernel bracket at x_mid, widened by the
+// group's half width, is conservative.  The exact per-sample test stays in the sweep.
+__device__ __forceinline__ void fill_node_records_x(const HistDev& H, const LatDev& L, const XGroupShared& sh, double t,
+                                                    int nz, int nzp, double* tab, int* jlo, int* jhi) {
+    const double hn = sh.x_half * sqrt(sh.nx * sh.nx + sh.ny * sh.ny) * (1.0 + 1e-9);
+    for (int n = threadIdx.x; n < sh.nreg * nzp; n += kXThreads) {
+        const int r = n / nzp, jj = n - r * nzp;
+        const Axis sa = sh.reg[r].sa;
+        const double sp = axis_node(sa, jj);                      // clamps past the last node
+        const double sp_prev = (jj > 0) ? axis_node(sa, jj - 1) : sp;
+        const double sp_next = axis_node(sa, jj + 1);
+        double v[6];
+        lattice_at(L, sp, v);
+        const double bx = sub_rn(sh.X0, v[0]), by = sub_rn(sh.Y0, v[1]);
+        double* o = tab + (size_t)n * kXRec;
+        o[0] = bx; o[1] = by; o[2] = v[2]; o[3] = v[3]; o[4] = v[4]; o[5] = v[5];
+        o[6] = curvature_at(L, sp); o[7] = sp;
+        o[8] = (jj < nz) ? 0.5 * ((sp_next - sp) + (sp - sp_prev)) : 0.0;
+        o[9] = 0.0;
+        if (jj < nz && sh.reg[r].ilo <= sh.reg[r].ihi) {
+            const double Cx = bx + sh.x_mid * sh.nx, Cy = by + sh.x_mid * sh.ny;
+            const double xa = axis_node(sh.reg[r].xa, sh.reg[r].ilo), xb = axis_node(sh.reg[r].xa, sh.reg[r].ihi);
+            const double ax = Cx - xa * v[2], ay = Cy - xa * v[3];
+            const double cx = Cx - xb * v[2], cy = Cy - xb * v[3];
+            const double ra = sqrt(ax * ax + ay * ay), rb = sqrt(cx * cx + cy * cy);
+            double r_max = fmax(ra, rb), r_min = fmin(ra, rb);
+            const double nn = v[2] * v[2] + v[3] * v[3];
+            const double xs = (Cx * v[2] + Cy * v[3]) / nn;
+            if (!(xs <= fmin(xa, xb)) && !(xs >= fmax(xa, xb))) {     // foot point inside (or undecidable)
+                const double fx = Cx - xs * v[2], fy = Cy - xs * v[3];
+                r_min = fmin(r_min, sqrt(fx * fx + fy * fy));
+            }
+            r_max = r_max * (1.0 + 1e-12) + hn;
+            r_min = fmax(0.0, r_min * (1.0 - 1e-12) - hn);
+            const double m = 1e-3;
+            const double ut_lo = ((t - r_max) - H.min_t) * H.inv_dt, ut_hi = ((t - r_min) - H.min_t) * H.inv_dt;
+            const double uz_lo = ((sp - (t - r_min)) - H.min_z) * H.inv_dz, uz_hi = ((sp - (t - r_max)) - H.min_z) * H.inv_dz;
+            const bool outside = (fmax(ut_lo, ut_hi) <= -1.0 - m) || (fmin(ut_lo, ut_hi) >= (double)H.T + m) ||
+                                 (fmax(uz_lo, uz_hi) <= -1.0 - m) || (fmin(uz_lo, uz_hi) >= (double)H.Z + m);
+            const bool certain = (ut_lo == ut_lo) && (ut_hi == ut_hi) && (uz_lo == uz_lo) && (uz_hi == uz_hi);   // no NaN
+            if (!(outside && certain)) {
+                atomicMin(jlo + r, jj);
+                atomicMax(jhi + r, jj);
+            }
+        }
+    }
+}
+
+// the two results of the group's points (CSR.py:588-589), x-major flattening of the mesh (CSR.py:382-389)
+__device__ __forceinline__ void xgroup_store(const MeshSrc& M, const dfcsr_wake_params& wp, const PeerOut& peers,
+                                             double* out_dE, double* out_kick, int ix, int iz, bool lane_valid,
+                                             double z, double xk) {
+    const double v_dE = -wp.csr_scaling * z;
+    const double v_kick = wp.csr_scaling * xk;
+    const long long idx = (long long)ix * M.mz.n + iz;
+    if (!lane_valid) return;
+    if (out_dE) out_dE[idx] = v_dE;
+    if (out_kick) out_kick[idx] = v_kick;
+#pragma unroll
+    for (int p = 0; p < DFCSR_MAX_PEERS; ++p) {
+        if (p < peers.n) {
+            peers.grid[p][idx] = v_dE;
+            peers.grid[p][peers.n_total + idx] = v_kick;
+        }
+    }
+}
+
+template <bool kF32>
+__global__ void __launch_bounds__(kXThreads, 2)
+wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupArgs A, double* __restrict__ out_dE,
+                   double* __restrict__ out_kick, unsigned long long* counters, const PeerOut peers) {
+    constexpr int VB = kF32 ? DFCSR_VOXEL_FLOATS * 4 : DFCSR_VOXEL_DOUBLES * 8;   // bytes per voxel
+    __shared__ XGroupShared sh;
+    extern __shared__ double2 node_tab2[];                 // [nreg * nzp][kXRec] doubles, 16-byte aligned records
+    double* const node_tab = reinterpret_cast<double*>(node_tab2);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    // CTAs are numbered chunk-major: the first wave spreads over all groups, and a CTA that starts later joins the
+    // group after the one its predecessor joined
+    const int gl = (int)(blockIdx.x % (unsigned)A.ngroups);           // group of this launch
+    const long long g = A.group_first + (long long)gl * A.group_stride;
+    const int ngx = (M.mx.n + 31) >> 5;
+    const int iz = (int)(g / ngx), gx = (int)(g - (long long)iz * ngx);
+    const int ix = gx * 32 + lane;
+    const bool lane_valid = ix < M.mx.n;
+    const int nz = wp.nz;
+    const int nzp = (nz + 31) & ~31;
+
+    // ---- set-up 1: the group's s, its rectangles and the list of pruned x' nodes ---------------------
+    const double zz = axis_node(M.mz, iz);
+    const double shift = __dadd_rn(__dmul_rn(M.slope, zz), M.intercept);
+    if (threadIdx.x == 0) {
+        const double s = wp.t + zz;                       // CSR.py:412
+        const int ix_hi = min(gx * 32 + 31, M.mx.n - 1);
+        const double xa = __dadd_rn(axis_node(M.mx, gx * 32), shift), xb = __dadd_rn(axis_node(M.mx, ix_hi), shift);
+        sh.s = s;
+        sh.x_mid = 0.5 * (xa + xb);
+        sh.x_half = 0.5 * fabs(xb - xa);
+        int nreg;
+        build_regions(wp, H, s, sh.x_mid, sh.reg, nreg);   // |slope0| <= 1 (launcher): the rectangles do not depend on x
+        sh.nreg = nreg;
+        int base = 0;
+        for (int r = 0; r < nreg; ++r) {
+            sh.node_base[r] = base;
+            base += max(0, sh.reg[r].ihi - sh.reg[r].ilo + 1);
+        }
+        for (int r = nreg; r <= kMaxRegions; ++r) sh.node_base[r] = base;
+        for (int r = 0; r < kMaxRegions; ++r) { sh.jlo[r] = INT_MAX; sh.jhi[r] = -1; }
+        double v[6];
+        lattice_at(L, s, v);
+        sh.X0 = v[0]; sh.Y0 = v[1]; sh.nx = v[2]; sh.ny = v[3]; sh.tx = v[4]; sh.ty = v[5];
+        // nothing left to do for this group?  (a late CTA of a group whose queue has run dry)
+        const int total = base, nun = (total + A.unit_nodes - 1) / A.unit_nodes;
+        sh.skip = (nun > 0 && *reinterpret_cast<volatile unsigned int*>(A.tickets + 2 * gl) >= (unsigned)nun) ? 1 : 0;
+    }
+    __syncthreads();
+    if (sh.skip) return;
+    const int nreg = sh.nreg;
+    fill_node_records_x(H, L, sh, wp.t, nz, nzp, node_tab, sh.jlo, sh.jhi);
+
+    // ---- per-lane constants of the lane's observation point (CSR.py:608-613, 645, 716-717) -----------
+    const double x_obs = __dadd_rn(axis_node(M.mx, min(ix, M.mx.n - 1)), shift);
+    const double Pt = wp.t, Pnx = sh.nx, Pny = sh.ny;
+    double Pvx, Pvy;
+    {
+        double f[5];
+        const double ut = (wp.t - H.min_t) * H.inv_dt, uy = (x_obs - H.min_x) * H.inv_dx;
+        const double uz = ((sh.s - wp.t) - H.min_z) * H.inv_dz;
+        const double vx = gather5<kF32>(H, ut, uy, uz, f) ? f[3] : 0.0;
+        Pvx = add_rn(sh.tx, mul_rn(vx, Pnx));              // vs*tau + vx*n with vs = 1
+        Pvy = add_rn(sh.ty, mul_rn(vx, Pny));
+    }
+    const double xnx = mul_rn(x_obs, Pnx), xny = mul_rn(x_obs, Pny);
+    __syncthreads();
+
+    const char* const ring = reinterpret_cast<const char*>(H.ring);
+    const unsigned slice_bytes = (unsigned)H.slice_elems * (kF32 ? 4u : 8u);   // < 2^32, checked by the launcher
+    const unsigned row_bytes = (unsigned)H.Z * (unsigned)VB;
+    const int total_nodes = sh.node_base[nreg];
+    const int U = A.unit_nodes;
+    const int nunits = (total_nodes + U - 1) / U;
+    double* const gpart = A.partials + (size_t)gl * A.max_units * 64;
+    unsigned long long n_in = 0;
+
+    unsigned int* const q_next = A.tickets + 2 * gl;
+    unsigned int* const q_done = A.tickets + 2 * gl + 1;
+    if (nunits == 0) {                               // no x' node can reach the grid: the wakes of the group are zero
+        if (blockIdx.x < (unsigned)A.ngroups && warp == 0) xgroup_store(M, wp, peers, out_dE, out_kick, ix, iz, lane_valid, 0.0, 0.0);
+        return;
+    }
+    for (;;) {
+        unsigned int qi = 0;
+        if (lane == 0) qi = atomicAdd(q_next, 1u);
+        qi = __shfl_sync(0xffffffffu, qi, 0);
+        if (qi >= (unsigned)nunits) break;
+        const int u = nunits - 1 - (int)qi;          // the near rectangle (last in the list, a reload at every step) first
+        double acc_z = 0.0, acc_x = 0.0;
+        const int n_end = min(total_nodes, (u + 1) * U);
+        for (int n = u * U; n < n_end; ++n) {
+            int r = 0;
+            while (r + 1 < nreg && n >= sh.node_base[r + 1]) ++r;
+            const int i = sh.reg[r].ilo + (n - sh.node_base[r]);
+            const Axis xa = sh.reg[r].xa;
+            const double xv = axis_node(xa, i);
+            const double uy = (xv - H.min_x) * H.inv_dx;
+            if (!cell_valid(uy, H.X)) continue;               // warp-uniform
+            int y0, y1;
+            double yd;
+            cell_split(uy, H.X, y0, y1, yd);
+            const double wy0 = 1.0 - yd;
+            const double x_prev = (i > 0) ? axis_node(xa, i - 1) : xv;
+            const double x_next = axis_node(xa, i + 1);
+            const double wx = 0.5 * ((x_next - xv) + (xv - x_prev));
+            const char* const row0 = ring + (size_t)((unsigned)y0 * (unsigned long long)row_bytes);
+            const char* const row1 = ring + (size_t)((unsigned)y1 * (unsigned long long)row_bytes);
+            const int j_lo = sh.jlo[r], j_hi = sh.jhi[r];
+            if (j_lo > j_hi) continue;                          // no s' node of this rectangle reaches the grid
+            const double2* rec = node_tab2 + (size_t)(r * nzp + j_lo) * (kXRec / 2);
+            double Yc[4][5];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int q = 0; q < 5; ++q) Yc[c][q] = 0.0;
+            int ct = INT_MIN, cz = INT_MIN;
+            for (int j = j_lo; j <= j_hi; ++j, rec += kXRec / 2) {
+                const double2 r01 = rec[0], r23 = rec[1], r45 = rec[2], r67 = rec[3], r89 = rec[4];
+                const double nxp = r23.x, nyp = r23.y, sp = r67.y;
+                const double Cx = add_rn(r01.x, xnx), Cy = add_rn(r01.y, xny);   // (R0(s) - R0(s')) + x n(s)
+                const double rx = sub_rn(Cx, mul_rn(xv, nxp));                  // reference rounding order (CSR.py:645-647)
+                const double ry = sub_rn(Cy, mul_rn(xv, nyp));
+                const double r2 = add_rn(mul_rn(rx, rx), mul_rn(ry, ry));
+                double rr, ir;
+                const bool fast = sqrt_pair_fast(r2, rr, ir);
+                if (!fast) {                                        // exceptional exponents (r = 0, inf, NaN): library path
+                    ir = rsqrt(r2);
+                    rr = __dsqrt_rn(r2);
+                }
+                const double t_ret = Pt - rr;
+                const double ut = (t_ret - H.min_t) * H.inv_dt;
+                const double uz = ((sp - t_ret) - H.min_z) * H.inv_dz;
+                const bool ok = lane_valid && cell_valid(ut, H.T) && cell_valid(uz, H.Z);
+                const unsigned okm = __ballot_sync(0xffffffffu, ok);
+                if (okm == 0u) continue;
+                n_in += (unsigned)__popc(okm);
+                int t0 = ok ? __double2int_rz(ut) : ct;
+                int z0 = ok ? __double2int_rz(uz) : cz;
+                const double td = ut - (double)t0;
+                double zd = uz - (double)z0;
+                if (z0 == H.Z - 1) { z0 = H.Z - 2; zd = 1.0; }      // clamp cell: same voxel, weight exactly 1
+                if (t0 != ct || z0 != cz) {                         // this lane entered another cell: reload its corners
+                    int s0 = H.head + t0;
+                    s0 -= (s0 >= H.cap) ? H.cap : 0;
+                    int s1 = s0 + 1;
+                    s1 = (s1 == H.cap) ? 0 : s1;
+                    s1 = (t0 == H.T - 1) ? s0 : s1;
+                    const unsigned zoff = (unsigned)z0 * (unsigned)VB;
+                    const size_t o0 = (size_t)((unsigned long long)(unsigned)s0 * slice_bytes + zoff);
+                    const size_t o1 = (size_t)((unsigned long long)(unsigned)s1 * slice_bytes + zoff);
+                    yblend_zrun<kF32>(row0 + o0, row1 + o0, wy0, yd, Yc[0], Yc[1]);
+                    yblend_zrun<kF32>(row0 + o1, row1 + o1, wy0, yd, Yc[2], Yc[3]);
+                    ct = t0;
+                    cz = z0;
+                }
+                const double wt0 = 1.0 - td, wz0 = 1.0 - zd;
+                const double w00 = wt0 * wz0, w01 = wt0 * zd, w10 = td * wz0, w11 = td * zd;
+                double fld[5];
+#pragma unroll
+                for (int q = 0; q < 5; ++q)
+                    fld[q] = fma(w11, Yc[3][q], fma(w10, Yc[2][q], fma(w01, Yc[1][q], w00 * Yc[0][q])));
+                // ---- integrand algebra (CSR.py:713-775), same operation order as integrand_algebra() ----
+                const double txp = r45.x, typ = r45.y, kappa = r67.x, ws = r89.x;
+                double scale = 1.0, gz = fld[2];
+                if (kappa != 0.0) {
+                    scale = add_rn(1.0, mul_rn(xv, kappa));
+                    gz = div_newton(fld[2], scale);
+                }
+                const double dnx = Pnx - nxp, dny = Pny - nyp;
+                const double q2 = add_rn(mul_rn(Pnx, txp), mul_rn(Pny, typ));
+                const double rho = fld[0], rho_x = fld[1], vxr = fld[3], vxx = fld[4];
+                const double vrx = add_rn(txp, mul_rn(vxr, nxp));            // velocity_ret
+                const double vry = add_rn(typ, mul_rn(vxr, nyp));
+                const double gxx = add_rn(mul_rn(rho_x, nxp), mul_rn(gz, txp));   // nabla_density_ret
+                const double gyy = add_rn(mul_rn(rho_x, nyp), mul_rn(gz, typ));
+                const double dot = add_rn(mul_rn(Pvx, vrx), mul_rn(Pvy, vry));  // part1
+                const double ax = mul_rn(sub_rn(Pvx, mul_rn(dot, vrx)), gxx);
+                const double ay = mul_rn(sub_rn(Pvy, mul_rn(dot, vry)), gyy);
+                const double num1 = mul_rn(scale, add_rn(ax, ay));
+                const double num2 = mul_rn(mul_rn(mul_rn(-scale, dot), rho), vxx);
+                const double Iz = add_rn(mul_rn(num1, ir), mul_rn(num2, ir));
+                const double q1 = add_rn(mul_rn(rx, dnx), mul_rn(ry, dny));   // (r - r').(n - n')
+                const double drho = sub_rn(-add_rn(mul_rn(vrx, gxx), mul_rn(vry, gyy)), mul_rn(rho, vxx));
+                const double sq1 = mul_rn(scale, q1);
+                const double ir2 = mul_rn(ir, ir);
+                const double w1 = mul_rn(mul_rn(sq1, mul_rn(ir2, ir)), rho);
+                const double w2 = mul_rn(mul_rn(sq1, ir2), drho);
+                const double w3 = mul_rn(mul_rn(mul_rn(-scale, q2), ir), drho);
+                const double Ix = add_rn(add_rn(w1, w2), w3);
+                const double w = ws * wx;
+                if (ok) {
+                    acc_z = fma(w, Iz, acc_z);
+                    acc_x = fma(w, Ix, acc_x);
+                }
+            }
+        }
+        __stcg(gpart + (size_t)u * 64 + lane, acc_z);
+        __stcg(gpart + (size_t)u * 64 + 32 + lane, acc_x);
+        __threadfence();
+        __syncwarp();
+        unsigned int done = 0;
+        if (lane == 0) done = atomicAdd(q_done, 1u);
+        done = __shfl_sync(0xffffffffu, done, 0);
+        if (done == (unsigned)nunits - 1u) {
+            // this was the group's last unit: add the unit sums in unit order (loads first, adds in order)
+            __threadfence();
+            double z = 0.0, xk = 0.0;
+            int v = 0;
+            for (; v + 4 <= nunits; v += 4) {
+                const double* p = gpart + (size_t)v * 64 + lane;
+                const double a0 = __ldcg(p), a1 = __ldcg(p + 64), a2 = __ldcg(p + 128), a3 = __ldcg(p + 192);
+                const double b0 = __ldcg(p + 32), b1 = __ldcg(p + 96), b2 = __ldcg(p + 160), b3 = __ldcg(p + 224);
+                z += a0; z += a1; z += a2; z += a3;
+                xk += b0; xk += b1; xk += b2; xk += b3;
+            }
+            for (; v < nunits; ++v) {
+                z += __ldcg(gpart + (size_t)v * 64 + lane);
+                xk += __ldcg(gpart + (size_t)v * 64 + 32 + lane);
+            }
+            xgroup_store(M, wp, peers, out_dE, out_kick, ix, iz, lane_valid, z, xk);
+            if (lane == 0 && counters) {
+                unsigned long long full = 0;
+                for (int r = 0; r < nreg; ++r) full += (unsigned long long)sh.reg[r].xa.n * (unsigned long long)nz;
+                atomicAdd(counters + 1, full * (unsigned long long)min(32, M.mx.n - gx * 32));
+            }
+        }
+    }
+    if (counters && lane == 0 && n_in) {
+        atomicAdd(counters + 0, n_in);
+        atomicAdd(counters + 2, n_in);
+    }
+}

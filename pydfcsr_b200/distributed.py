@@ -53,6 +53,26 @@ def all_gather_blocks(send: torch.Tensor, count, n: int) -> torch.Tensor:
     return torch.cat([recv[p, :, :count[p]] for p in range(world)], dim=1)
 
 
+def xgroup_owner(nx: int, nz: int, world: int, device) -> torch.Tensor:
+    """Rank that computes mesh point (ix, iz) when x-groups are dealt out round-robin (group = iz * ceil(nx/32) + ix // 32,
+    flat index = ix * nz + iz as in get_CSR_mesh, CSR.py:382-389)."""
+    ix = torch.arange(nx, device=device).unsqueeze(1)
+    iz = torch.arange(nz, device=device).unsqueeze(0)
+    return ((iz * ((nx + 31) // 32) + ix // 32) % world).reshape(-1)
+
+
+def all_gather_select(mine: torch.Tensor, owner: torch.Tensor) -> torch.Tensor:
+    """mine: (F, n) with this rank's points filled in.  Returns (F, n) where point k is taken from rank owner[k]
+    (an exact exchange: bits are copied, nothing is added)."""
+    world = dist.get_world_size()
+    fields, n = mine.shape
+    flat = torch.empty(world * fields * n, dtype=mine.dtype, device=mine.device)
+    dist.all_gather_into_tensor(flat, mine.contiguous().view(-1))
+    recv = flat.view(world, fields, n)
+    idx = owner.view(1, 1, n).expand(1, fields, n)
+    return torch.gather(recv, 0, idx)[0]
+
+
 class PeerWakeGrid:
     """Wake grids of all ranks mapped into every rank (NVLink peer memory) for the fused K4 + exchange.
 

@@ -524,6 +524,47 @@ def wake_grid_peers(hist: DeviceHistory, lat: DeviceLattice, wp: _lib.WakeParams
           "dfcsr_wake_grid_peers")
 
 
+def wake_xgroup_plan(hist: DeviceHistory, wp: _lib.WakeParams, x_axis: Axis, z_axis: Axis) -> _lib.XGroupPlan:
+    """Plan of the x-group mapping for this step (dfcsr_wake_xgroup_plan); `n_groups == 0`: use wake_grid."""
+    hv = hist.view()
+    plan = _lib.XGroupPlan()
+    check(lib.dfcsr_wake_xgroup_plan(C.byref(hv), C.byref(wp), x_axis, z_axis, C.byref(plan)), "dfcsr_wake_xgroup_plan")
+    return plan
+
+
+_XGROUP_WS: dict = {}
+
+
+def xgroup_workspace(device, nbytes: int) -> torch.Tensor:
+    """Zero-initialised scratch of the x-group kernel, one per device, grown on demand (the kernel leaves its ticket
+    words zero, so the block is reusable from launch to launch on one stream)."""
+    ws = _XGROUP_WS.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = _XGROUP_WS[device] = torch.zeros(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
+    return ws
+
+
+def wake_grid_xgroups(hist: DeviceHistory, lat: DeviceLattice, wp: _lib.WakeParams, x_axis: Axis, z_axis: Axis, slope,
+                      intercept, plan: _lib.XGroupPlan, group_first=0, group_count=None, group_stride=1, out=None,
+                      peer_ptrs=None, counters=None):
+    """K4 with one lane per observation point (dfcsr_wake_grid_xgroups): groups group_first, group_first + stride, ...
+    are computed here; results land at their mesh index of the FULL (2, N) `out` and / or of every peer grid."""
+    n = x_axis.n * z_axis.n
+    if group_count is None:
+        group_count = (plan.n_groups - group_first + group_stride - 1) // group_stride
+    dev = hist.ring.device
+    if out is None and peer_ptrs is None:
+        out = torch.zeros((2, n), dtype=F64, device=dev)
+    ws = xgroup_workspace(dev, group_count * plan.workspace_bytes_per_group)
+    hv, lv = hist.view(), lat.view()
+    check(lib.dfcsr_wake_grid_xgroups(C.byref(hv), C.byref(lv), C.byref(wp), x_axis, z_axis, float(slope), float(intercept),
+                                      int(group_first), int(group_count), int(group_stride),
+                                      _ptr(out[0]) if out is not None else None, _ptr(out[1]) if out is not None else None,
+                                      peer_ptrs, len(peer_ptrs) if peer_ptrs is not None else 0, _ptr(ws), ws.numel(),
+                                      _ptr(counters), _stream()), "dfcsr_wake_grid_xgroups")
+    return (out[0], out[1]) if out is not None else None
+
+
 def wake_uses_skipping(hist: DeviceHistory, wp: _lib.WakeParams) -> bool:
     """Whether a wake launch on this history with these beam scalars selects zero-density skipping."""
     hv = hist.view()
