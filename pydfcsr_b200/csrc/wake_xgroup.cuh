@@ -30,7 +30,7 @@
 #pragma once
 // (included INSIDE namespace dfcsr of wake.cu, after the shared device helpers)
 
-constexpr int kXRec = 10;          // base_x, base_y, n'x, n'y, tau'x, tau'y, kappa, s', w_s, pad: 80 B, five LDS.128
+constexpr int kXRec = 12;          // base_x, base_y, n'x, n'y, tau'x, tau'y, kappa, s', w_s, n-n' (2), n.tau': 96 B, six LDS.128
 constexpr int kXThreads = 256;
 constexpr int kXWarps = kXThreads / 32;
 
@@ -53,7 +53,7 @@ struct XGroupArgs {
     unsigned int* tickets;                 // [groups of the launch][2] = {units handed out, units finished}; zeroed by the launcher
 };
 
-// the s'-only constants of every node of every rectangle as 80-byte records with base = R0(s) - R0(s') instead of the
+// the s'-only constants of every node of every rectangle as 96-byte records with base = R0(s) - R0(s') instead of the
 // point's C = base + x n(s) (CSR.py:645: the lanes add their own x n(s)), and the bracket of the s' nodes that can reach
 // the history grid for ANY x' of the pruned range and ANY x of the group: r(x, x') = |base + x n - x' n'| differs from
 // r(x_mid, x') by at most |x - x_mid| |n| (triangle inequality), so the point-kernel bracket at x_mid, widened by the
@@ -61,6 +61,7 @@ struct XGroupArgs {
 __device__ __forceinline__ void fill_node_records_x(const HistDev& H, const LatDev& L, const XGroupShared& sh, double t,
                                                     int nz, int nzp, double* tab, int* jlo, int* jhi) {
     const double hn = sh.x_half * sqrt(sh.nx * sh.nx + sh.ny * sh.ny) * (1.0 + 1e-9);
+    if (threadIdx.x < kXRec) tab[(size_t)sh.nreg * nzp * kXRec + threadIdx.x] = 0.0;   // pad record: the pipelined sweep reads one node ahead
     for (int n = threadIdx.x; n < sh.nreg * nzp; n += kXThreads) {
         const int r = n / nzp, jj = n - r * nzp;
         const Axis sa = sh.reg[r].sa;
@@ -74,7 +75,9 @@ __device__ __forceinline__ void fill_node_records_x(const HistDev& H, const LatD
         o[0] = bx; o[1] = by; o[2] = v[2]; o[3] = v[3]; o[4] = v[4]; o[5] = v[5];
         o[6] = curvature_at(L, sp); o[7] = sp;
         o[8] = (jj < nz) ? 0.5 * ((sp_next - sp) + (sp - sp_prev)) : 0.0;
-        o[9] = 0.0;
+        o[9] = sh.nx - v[2];                                      // n(s) - n(s') and n(s) . tau(s') (CSR.py:757-760)
+        o[10] = sh.ny - v[3];
+        o[11] = add_rn(mul_rn(sh.nx, v[4]), mul_rn(sh.ny, v[5]));
         if (jj < nz && sh.reg[r].ilo <= sh.reg[r].ihi) {
             const double Cx = bx + sh.x_mid * sh.nx, Cy = by + sh.x_mid * sh.ny;
             const double xa = axis_node(sh.reg[r].xa, sh.reg[r].ilo), xb = axis_node(sh.reg[r].xa, sh.reg[r].ihi);
@@ -123,13 +126,13 @@ __device__ __forceinline__ void xgroup_store(const MeshSrc& M, const dfcsr_wake_
     }
 }
 
-template <bool kF32>
+template <bool kF32, bool kPipe>
 __global__ void __launch_bounds__(kXThreads, 2)
 wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupArgs A, double* __restrict__ out_dE,
                    double* __restrict__ out_kick, unsigned long long* counters, const PeerOut peers) {
     constexpr int VB = kF32 ? DFCSR_VOXEL_FLOATS * 4 : DFCSR_VOXEL_DOUBLES * 8;   // bytes per voxel
     __shared__ XGroupShared sh;
-    extern __shared__ double2 node_tab2[];                 // [nreg * nzp][kXRec] doubles, 16-byte aligned records
+    extern __shared__ double2 node_tab2[];                 // [nreg * nzp + 1][kXRec] doubles, 16-byte aligned records
     double* const node_tab = reinterpret_cast<double*>(node_tab2);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -199,6 +202,7 @@ wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupA
     const int nunits = (total_nodes + U - 1) / U;
     double* const gpart = A.partials + (size_t)gl * A.max_units * 64;
     unsigned long long n_in = 0;
+    const int Zm1 = H.Z - 1, Tm1 = H.T - 1;
 
     unsigned int* const q_next = A.tickets + 2 * gl;
     unsigned int* const q_done = A.tickets + 2 * gl + 1;
@@ -240,37 +244,43 @@ wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupA
 #pragma unroll
                 for (int q = 0; q < 5; ++q) Yc[c][q] = 0.0;
             int ct = INT_MIN, cz = INT_MIN;
-            for (int j = j_lo; j <= j_hi; ++j, rec += kXRec / 2) {
-                const double2 r01 = rec[0], r23 = rec[1], r45 = rec[2], r67 = rec[3], r89 = rec[4];
-                const double nxp = r23.x, nyp = r23.y, sp = r67.y;
+            // 1 + x' kappa and its reciprocal change only where the curvature does (piecewise constant along s')
+            double kprev = 0.0, scale = 1.0, rscale = 1.0;
+            unsigned n_node = 0;
+
+            // geometry of the sample at node record `q` (CSR.py:645-650): r - r', r^2 and, for ordinary exponents, r and
+            // 1/r -- branch-free, so that the compiler may interleave this dependent chain with independent work
+            auto geometry = [&](const double2* q, double& rx, double& ry, double& r2, double& rr, double& ir) -> bool {
+                const double2 r01 = q[0], r23 = q[1];
                 const double Cx = add_rn(r01.x, xnx), Cy = add_rn(r01.y, xny);   // (R0(s) - R0(s')) + x n(s)
-                const double rx = sub_rn(Cx, mul_rn(xv, nxp));                  // reference rounding order (CSR.py:645-647)
-                const double ry = sub_rn(Cy, mul_rn(xv, nyp));
-                const double r2 = add_rn(mul_rn(rx, rx), mul_rn(ry, ry));
-                double rr, ir;
-                const bool fast = sqrt_pair_fast(r2, rr, ir);
-                if (!fast) {                                        // exceptional exponents (r = 0, inf, NaN): library path
+                rx = sub_rn(Cx, mul_rn(xv, r23.x));                             // reference rounding order
+                ry = sub_rn(Cy, mul_rn(xv, r23.y));
+                r2 = add_rn(mul_rn(rx, rx), mul_rn(ry, ry));
+                return sqrt_pair_fast(r2, rr, ir);
+            };
+            // exceptional exponents (r = 0, inf, NaN: library path), then the fractional cell coordinates
+            auto locate = [&](const double2* q, bool fast, double r2, double rr, double& ir, double& ut, double& uz) {
+                if (!fast) {
                     ir = rsqrt(r2);
                     rr = __dsqrt_rn(r2);
                 }
                 const double t_ret = Pt - rr;
-                const double ut = (t_ret - H.min_t) * H.inv_dt;
-                const double uz = ((sp - t_ret) - H.min_z) * H.inv_dz;
-                const bool ok = lane_valid && cell_valid(ut, H.T) && cell_valid(uz, H.Z);
-                const unsigned okm = __ballot_sync(0xffffffffu, ok);
-                if (okm == 0u) continue;
-                n_in += (unsigned)__popc(okm);
+                ut = (t_ret - H.min_t) * H.inv_dt;
+                uz = ((q[3].y - t_ret) - H.min_z) * H.inv_dz;
+            };
+            // the five fields at (ut, uz) from the lane's cached corners, reloading them when the lane changed cell
+            auto gather = [&](double ut, double uz, bool ok, double (&fld)[5]) {
                 int t0 = ok ? __double2int_rz(ut) : ct;
                 int z0 = ok ? __double2int_rz(uz) : cz;
                 const double td = ut - (double)t0;
                 double zd = uz - (double)z0;
-                if (z0 == H.Z - 1) { z0 = H.Z - 2; zd = 1.0; }      // clamp cell: same voxel, weight exactly 1
-                if (t0 != ct || z0 != cz) {                         // this lane entered another cell: reload its corners
+                if (z0 == Zm1) { z0 = Zm1 - 1; zd = 1.0; }      // clamp cell: same voxel, weight exactly 1
+                if (t0 != ct || z0 != cz) {
                     int s0 = H.head + t0;
                     s0 -= (s0 >= H.cap) ? H.cap : 0;
                     int s1 = s0 + 1;
                     s1 = (s1 == H.cap) ? 0 : s1;
-                    s1 = (t0 == H.T - 1) ? s0 : s1;
+                    s1 = (t0 == Tm1) ? s0 : s1;
                     const unsigned zoff = (unsigned)z0 * (unsigned)VB;
                     const size_t o0 = (size_t)((unsigned long long)(unsigned)s0 * slice_bytes + zoff);
                     const size_t o1 = (size_t)((unsigned long long)(unsigned)s1 * slice_bytes + zoff);
@@ -281,19 +291,16 @@ wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupA
                 }
                 const double wt0 = 1.0 - td, wz0 = 1.0 - zd;
                 const double w00 = wt0 * wz0, w01 = wt0 * zd, w10 = td * wz0, w11 = td * zd;
-                double fld[5];
 #pragma unroll
                 for (int q = 0; q < 5; ++q)
                     fld[q] = fma(w11, Yc[3][q], fma(w10, Yc[2][q], fma(w01, Yc[1][q], w00 * Yc[0][q])));
-                // ---- integrand algebra (CSR.py:713-775), same operation order as integrand_algebra() ----
-                const double txp = r45.x, typ = r45.y, kappa = r67.x, ws = r89.x;
-                double scale = 1.0, gz = fld[2];
-                if (kappa != 0.0) {
-                    scale = add_rn(1.0, mul_rn(xv, kappa));
-                    gz = div_newton(fld[2], scale);
-                }
-                const double dnx = Pnx - nxp, dny = Pny - nyp;
-                const double q2 = add_rn(mul_rn(Pnx, txp), mul_rn(Pny, typ));
+            };
+            // integrand algebra (CSR.py:713-775), same operation order as integrand_algebra(), and the quadrature sums
+            auto algebra = [&](const double2* q, const double (&fld)[5], double rx, double ry, double ir, bool ok) {
+                const double2 r23 = q[1], r45 = q[2], r89 = q[4], rab = q[5];
+                const double nxp = r23.x, nyp = r23.y, txp = r45.x, typ = r45.y, ws = r89.x;
+                const double gz = div_by(fld[2], scale, rscale);   // rho_z / scale (exactly rho_z where kappa = 0)
+                const double dnx = r89.y, dny = rab.x, q2 = rab.y;
                 const double rho = fld[0], rho_x = fld[1], vxr = fld[3], vxx = fld[4];
                 const double vrx = add_rn(txp, mul_rn(vxr, nxp));            // velocity_ret
                 const double vry = add_rn(typ, mul_rn(vxr, nyp));
@@ -318,7 +325,56 @@ wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupA
                     acc_z = fma(w, Iz, acc_z);
                     acc_x = fma(w, Ix, acc_x);
                 }
+            };
+            auto in_grid = [&](double ut, double uz) {               // interp3D.py:30-52
+                return lane_valid && (ut > -1.0) && (ut < H.Td) && (uz > -1.0) && (uz < H.Zd);
+            };
+            auto new_scale = [&](double kappa) {                     // warp-uniform, a few times per x' node
+                if (kappa != kprev) {
+                    kprev = kappa;
+                    scale = add_rn(1.0, mul_rn(xv, kappa));
+                    rscale = rcp_newton(scale);
+                }
+            };
+
+            if (kPipe) {
+                // Software pipeline: a GPU warp issues in order, and the geometry of a sample is one long dependent fp64
+                // chain (orbit difference -> r^2 -> rsqrt refinement -> r -> cell coordinates).  The geometry of node
+                // j + 1 is therefore issued in the same straight-line block as the integrand algebra of node j, which is
+                // independent of it; the gather of j + 1 (the only divergent part) follows.
+                double rx, ry, r2, rr, ir, ut, uz, fld[5];
+                bool fast = geometry(rec, rx, ry, r2, rr, ir);
+                locate(rec, fast, r2, rr, ir, ut, uz);
+                bool ok = in_grid(ut, uz);
+                n_node += (unsigned)__popc(__ballot_sync(0xffffffffu, ok));
+                new_scale(rec[3].x);
+                gather(ut, uz, ok, fld);
+                for (int j = j_lo; j <= j_hi; ++j, rec += kXRec / 2) {
+                    double rxn, ryn, irn;
+                    fast = geometry(rec + kXRec / 2, rxn, ryn, r2, rr, irn);   // node j + 1 (the table is padded by one record)
+                    algebra(rec, fld, rx, ry, ir, ok);                         // node j
+                    locate(rec + kXRec / 2, fast, r2, rr, irn, ut, uz);
+                    ok = in_grid(ut, uz) && (j < j_hi);
+                    n_node += (unsigned)__popc(__ballot_sync(0xffffffffu, ok));
+                    new_scale(rec[kXRec / 2 + 3].x);
+                    gather(ut, uz, ok, fld);
+                    rx = rxn; ry = ryn; ir = irn;
+                }
+            } else {
+                for (int j = j_lo; j <= j_hi; ++j, rec += kXRec / 2) {
+                    double rx, ry, r2, rr, ir, ut, uz, fld[5];
+                    const bool fast = geometry(rec, rx, ry, r2, rr, ir);
+                    locate(rec, fast, r2, rr, ir, ut, uz);
+                    const bool ok = in_grid(ut, uz);
+                    const unsigned okm = __ballot_sync(0xffffffffu, ok);
+                    if (okm == 0u) continue;
+                    n_node += (unsigned)__popc(okm);
+                    gather(ut, uz, ok, fld);
+                    new_scale(rec[3].x);
+                    algebra(rec, fld, rx, ry, ir, ok);
+                }
             }
+            n_in += n_node;
         }
         __stcg(gpart + (size_t)u * 64 + lane, acc_z);
         __stcg(gpart + (size_t)u * 64 + 32 + lane, acc_x);
