@@ -31,6 +31,7 @@
 // (included INSIDE namespace dfcsr of wake.cu, after the shared device helpers)
 
 constexpr int kXRec = 12;          // base_x, base_y, n'x, n'y, tau'x, tau'y, kappa, s', w_s, n-n' (2), n.tau': 96 B, six LDS.128
+constexpr int kXWin = 16;          // z nodes of a warp's window of transverse-blended history nodes (x 2 slices = 32 = one per lane)
 constexpr int kXThreads = 256;
 constexpr int kXWarps = kXThreads / 32;
 
@@ -107,6 +108,28 @@ __device__ __forceinline__ void fill_node_records_x(const HistDev& H, const LatD
     }
 }
 
+// one history voxel of both transverse rows, blended along the transverse axis (same operations as yblend_zrun)
+template <bool kF32>
+__device__ __forceinline__ void yblend_node(const char* __restrict__ pa, const char* __restrict__ pb, double wy0, double yd,
+                                            double (&out)[5]) {
+    if (kF32) {
+        const float w0 = (float)wy0, w1 = (float)yd;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(pa)), b = __ldg(reinterpret_cast<const float4*>(pb));
+        const float ca = __ldg(reinterpret_cast<const float*>(pa) + 4), cb = __ldg(reinterpret_cast<const float*>(pb) + 4);
+        out[0] = (double)fmaf(w1, b.x, w0 * a.x); out[1] = (double)fmaf(w1, b.y, w0 * a.y);
+        out[2] = (double)fmaf(w1, b.z, w0 * a.z); out[3] = (double)fmaf(w1, b.w, w0 * a.w);
+        out[4] = (double)fmaf(w1, cb, w0 * ca);
+    } else {
+        const double2* qa = reinterpret_cast<const double2*>(pa);
+        const double2* qb = reinterpret_cast<const double2*>(pb);
+        const double2 a0 = __ldg(qa), a1 = __ldg(qa + 1), b0 = __ldg(qb), b1 = __ldg(qb + 1);
+        const double ca = __ldg(reinterpret_cast<const double*>(pa) + 4), cb = __ldg(reinterpret_cast<const double*>(pb) + 4);
+        out[0] = fma(yd, b0.x, wy0 * a0.x); out[1] = fma(yd, b0.y, wy0 * a0.y);
+        out[2] = fma(yd, b1.x, wy0 * a1.x); out[3] = fma(yd, b1.y, wy0 * a1.y);
+        out[4] = fma(yd, cb, wy0 * ca);
+    }
+}
+
 // the two results of the group's points (CSR.py:588-589), x-major flattening of the mesh (CSR.py:382-389)
 __device__ __forceinline__ void xgroup_store(const MeshSrc& M, const dfcsr_wake_params& wp, const PeerOut& peers,
                                              double* out_dE, double* out_kick, int ix, int iz, bool lane_valid,
@@ -146,6 +169,8 @@ wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupA
     const bool lane_valid = ix < M.mx.n;
     const int nz = wp.nz;
     const int nzp = (nz + 31) & ~31;
+    // behind the node table: one 2 x kXWin window of 48-byte transverse-blended nodes per warp
+    double* const tile = node_tab + (size_t)kXRec * (3 * nzp + 1) + (size_t)warp * (2 * kXWin * 6);
 
     // ---- set-up 1: the group's s, its rectangles and the list of pruned x' nodes ---------------------
     const double zz = axis_node(M.mz, iz);
@@ -238,12 +263,8 @@ wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupA
             const int j_lo = sh.jlo[r], j_hi = sh.jhi[r];
             if (j_lo > j_hi) continue;                          // no s' node of this rectangle reaches the grid
             const double2* rec = node_tab2 + (size_t)(r * nzp + j_lo) * (kXRec / 2);
-            double Yc[4][5];
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-                for (int q = 0; q < 5; ++q) Yc[c][q] = 0.0;
-            int ct = INT_MIN, cz = INT_MIN;
+            // per-warp window of transverse-blended history nodes in shared memory: slices (tw, tw+1) x z nodes [zw, zw+16)
+            int tw = INT_MIN, zw = 0;
             // 1 + x' kappa and its reciprocal change only where the curvature does (piecewise constant along s')
             double kprev = 0.0, scale = 1.0, rscale = 1.0;
             unsigned n_node = 0;
@@ -268,14 +289,59 @@ wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupA
                 ut = (t_ret - H.min_t) * H.inv_dt;
                 uz = ((q[3].y - t_ret) - H.min_z) * H.inv_dz;
             };
-            // the five fields at (ut, uz) from the lane's cached corners, reloading them when the lane changed cell
+            // The five fields at (ut, uz).  All lanes of a step look at nearly the same place of the (t', z) plane (same x'
+            // and s' node, observation points 0.1 sigma_x apart), and the place moves slowly along the sweep: the warp keeps
+            // the transverse-blended nodes of a 2 x 16 window around it in shared memory (one node per lane when the window
+            // is refilled: 6 loads from the two history rows, 5 blends) and a sample is 4 corners x 40 B read from there.
+            // When the lanes that need a new window fit into one (same slice pair, z spread <= 14 cells), the window is
+            // moved (warp-uniform); a lane that is still outside (near the observer the spread exceeds the window) blends its
+            // corners from global memory with the same operations, so the bits do not depend on the path taken.
             auto gather = [&](double ut, double uz, bool ok, double (&fld)[5]) {
-                int t0 = ok ? __double2int_rz(ut) : ct;
-                int z0 = ok ? __double2int_rz(uz) : cz;
+                int t0 = ok ? __double2int_rz(ut) : tw;
+                int z0 = ok ? __double2int_rz(uz) : zw;
                 const double td = ut - (double)t0;
                 double zd = uz - (double)z0;
                 if (z0 == Zm1) { z0 = Zm1 - 1; zd = 1.0; }      // clamp cell: same voxel, weight exactly 1
-                if (t0 != ct || z0 != cz) {
+                bool inwin = (t0 == tw) && ((unsigned)(z0 - zw) <= (unsigned)(kXWin - 2));
+                if (__any_sync(0xffffffffu, ok && !inwin)) {
+                    const int zmin = __reduce_min_sync(0xffffffffu, ok ? z0 : INT_MAX);
+                    const int zmax = __reduce_max_sync(0xffffffffu, ok ? z0 : INT_MIN);
+                    const int tmin = __reduce_min_sync(0xffffffffu, ok ? t0 : INT_MAX);
+                    const int tmax = __reduce_max_sync(0xffffffffu, ok ? t0 : INT_MIN);
+                    if (tmin == tmax && zmax - zmin <= kXWin - 2) {
+                        tw = tmin;
+                        zw = max(0, min(zmin - ((kXWin - 2 - (zmax - zmin)) >> 1), H.Z - kXWin));
+                        // lane -> (slice tw or its successor, node zw + 0..15), clamped into the grid (clamped copies are
+                        // never read: a valid cell ends at node Z - 1)
+                        const int ti = lane >> 4, zn = min(zw + (lane & (kXWin - 1)), Zm1);
+                        int sl = H.head + ((ti && tw != Tm1) ? tw + 1 : tw);
+                        sl -= (sl >= H.cap) ? H.cap : 0;
+                        const size_t o = (size_t)((unsigned long long)(unsigned)sl * slice_bytes + (unsigned)zn * (unsigned)VB);
+                        double y[5];
+                        yblend_node<kF32>(row0 + o, row1 + o, wy0, yd, y);
+                        __syncwarp();
+                        double2* dst = reinterpret_cast<double2*>(tile + lane * 6);
+                        dst[0] = make_double2(y[0], y[1]);
+                        dst[1] = make_double2(y[2], y[3]);
+                        tile[lane * 6 + 4] = y[4];
+                        __syncwarp();
+                        inwin = ok;
+                    }
+                }
+                const double wt0 = 1.0 - td, wz0 = 1.0 - zd;
+                const double w00 = wt0 * wz0, w01 = wt0 * zd, w10 = td * wz0, w11 = td * zd;
+                double Y[4][5];
+                if (inwin || !ok) {
+                    const double* p = tile + (inwin ? (z0 - zw) * 6 : 0);
+                    const double2 a0 = *reinterpret_cast<const double2*>(p), a1 = *reinterpret_cast<const double2*>(p + 2);
+                    const double2 b0 = *reinterpret_cast<const double2*>(p + 6), b1 = *reinterpret_cast<const double2*>(p + 8);
+                    const double2 c0 = *reinterpret_cast<const double2*>(p + 96), c1 = *reinterpret_cast<const double2*>(p + 98);
+                    const double2 d0 = *reinterpret_cast<const double2*>(p + 102), d1 = *reinterpret_cast<const double2*>(p + 104);
+                    Y[0][0] = a0.x; Y[0][1] = a0.y; Y[0][2] = a1.x; Y[0][3] = a1.y; Y[0][4] = p[4];
+                    Y[1][0] = b0.x; Y[1][1] = b0.y; Y[1][2] = b1.x; Y[1][3] = b1.y; Y[1][4] = p[10];
+                    Y[2][0] = c0.x; Y[2][1] = c0.y; Y[2][2] = c1.x; Y[2][3] = c1.y; Y[2][4] = p[100];
+                    Y[3][0] = d0.x; Y[3][1] = d0.y; Y[3][2] = d1.x; Y[3][3] = d1.y; Y[3][4] = p[106];
+                } else {
                     int s0 = H.head + t0;
                     s0 -= (s0 >= H.cap) ? H.cap : 0;
                     int s1 = s0 + 1;
@@ -284,16 +350,12 @@ wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupA
                     const unsigned zoff = (unsigned)z0 * (unsigned)VB;
                     const size_t o0 = (size_t)((unsigned long long)(unsigned)s0 * slice_bytes + zoff);
                     const size_t o1 = (size_t)((unsigned long long)(unsigned)s1 * slice_bytes + zoff);
-                    yblend_zrun<kF32>(row0 + o0, row1 + o0, wy0, yd, Yc[0], Yc[1]);
-                    yblend_zrun<kF32>(row0 + o1, row1 + o1, wy0, yd, Yc[2], Yc[3]);
-                    ct = t0;
-                    cz = z0;
+                    yblend_zrun<kF32>(row0 + o0, row1 + o0, wy0, yd, Y[0], Y[1]);
+                    yblend_zrun<kF32>(row0 + o1, row1 + o1, wy0, yd, Y[2], Y[3]);
                 }
-                const double wt0 = 1.0 - td, wz0 = 1.0 - zd;
-                const double w00 = wt0 * wz0, w01 = wt0 * zd, w10 = td * wz0, w11 = td * zd;
 #pragma unroll
                 for (int q = 0; q < 5; ++q)
-                    fld[q] = fma(w11, Yc[3][q], fma(w10, Yc[2][q], fma(w01, Yc[1][q], w00 * Yc[0][q])));
+                    fld[q] = fma(w11, Y[3][q], fma(w10, Y[2][q], fma(w01, Y[1][q], w00 * Y[0][q])));
             };
             // integrand algebra (CSR.py:713-775), same operation order as integrand_algebra(), and the quadrature sums
             auto algebra = [&](const double2* q, const double (&fld)[5], double rx, double ry, double ir, bool ok) {

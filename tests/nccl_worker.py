@@ -12,13 +12,13 @@ from pydfcsr_b200 import CSR2D, synth  # noqa: E402
 elements = [(n, k, L, a, e1, e2, 1) for (n, k, L, a, e1, e2, _s) in synth.CHICANE_ELEMENTS]
 
 
-def make(parallel, shard, apply_csr):
+def make(parallel, shard, apply_csr, xbins=5, zbins=7):
     inp = {"input_beam": {"style": "synthetic", "n_particle": 100_000, "seed": 1},
            "input_lattice": {"lattice_config": synth.chicane_lattice_config(elements=elements)},
            "particle_deposition": dict(xbins=64, zbins=96, xlim=5, zlim=5, filter_order=1, filter_window=9,
                                        velocity_threhold=1000, upper_limit=2000),
            "CSR_integration": dict(n_formation_length=1, zbins=40, xbins=40),
-           "CSR_computation": dict(compute_CSR=1, apply_CSR=apply_csr, transverse_on=1, xbins=5, zbins=7, xlim=3, zlim=3,
+           "CSR_computation": dict(compute_CSR=1, apply_CSR=apply_csr, transverse_on=1, xbins=xbins, zbins=zbins, xlim=3, zlim=3,
                                    write_beam=None, write_wakes=False, workdir="/tmp/dfcsr_nccl")}
     return CSR2D(inp, parallel=parallel, verbose=False, shard_particles=shard)
 
@@ -72,5 +72,20 @@ if mode == "peers":                           # same run through the NCCL fallba
     alt.run(stop_time=0.45)
     assert torch.equal(alt.dE_dct, one.dE_dct) and torch.equal(alt.beam.coords[1], shd.beam.coords[1]), "NCCL shard exchange differs"
     os.environ["DFCSR_FUSED_GATHER"] = "1"
+# ---- a mesh row of 32 points: K4 runs in its x-group mapping (one lane per point); the groups are dealt out round-robin,
+# stored into all ranks' grids over peer memory (or gathered by NCCL), and the result must be bitwise the serial launch's
+xg = make(True, False, 0, xbins=32, zbins=5)
+xg.skip_mode = "off"
+xg.run(stop_time=0.25)
+assert xg.last_wake_mapping == "xgroup"
+par = (xg.dE_dct.clone(), xg.x_kick.clone())
+xg.calculate_2D_CSR()
+assert torch.equal(par[0], xg.dE_dct) and torch.equal(par[1], xg.x_kick), "x-groups: sharded != serial"
+assert float(par[0].abs().max()) > 0
+if xg._peer_grid is not None:
+    keep, xg._peer_grid = xg._peer_grid, None
+    xg.calculate_2D_CSR_parallel()
+    assert torch.equal(xg.dE_dct, par[0]) and torch.equal(xg.x_kick, par[1]), "x-groups: NCCL gather != fused exchange"
+    xg._peer_grid = keep
 os.write(1, f"nccl ok {csr.rank} exchange={path} shards={mode}\n".encode())   # one write per rank: print() pieces interleave
 torch.distributed.destroy_process_group()
