@@ -63,7 +63,7 @@ __device__ __forceinline__ void fill_node_records_x(const HistDev& H, const LatD
                                                     int nz, int nzp, double* tab, int* jlo, int* jhi) {
     const double hn = sh.x_half * sqrt(sh.nx * sh.nx + sh.ny * sh.ny) * (1.0 + 1e-9);
     if (threadIdx.x < kXRec) tab[(size_t)sh.nreg * nzp * kXRec + threadIdx.x] = 0.0;   // pad record: the pipelined sweep reads one node ahead
-    for (int n = threadIdx.x; n < sh.nreg * nzp; n += kXThreads) {
+    for (int n = threadIdx.x; n < sh.nreg * nzp; n += (int)blockDim.x) {
         const int r = n / nzp, jj = n - r * nzp;
         const Axis sa = sh.reg[r].sa;
         const double sp = axis_node(sa, jj);                      // clamps past the last node
@@ -108,6 +108,16 @@ __device__ __forceinline__ void fill_node_records_x(const HistDev& H, const LatD
     }
 }
 
+// shared-memory accesses by 32-bit shared-space address (volatile: kept in program order with each other)
+__device__ __forceinline__ void lds128(unsigned a, double& x, double& y) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+}
+__device__ __forceinline__ void lds64(unsigned a, double& x) { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(a)); }
+__device__ __forceinline__ void sts128(unsigned a, double x, double y) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ void sts64(unsigned a, double x) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(x) : "memory"); }
+
 // one history voxel of both transverse rows, blended along the transverse axis (same operations as yblend_zrun)
 template <bool kF32>
 __device__ __forceinline__ void yblend_node(const char* __restrict__ pa, const char* __restrict__ pb, double wy0, double yd,
@@ -149,13 +159,16 @@ __device__ __forceinline__ void xgroup_store(const MeshSrc& M, const dfcsr_wake_
     }
 }
 
-template <bool kF32, bool kPipe>
-__global__ void __launch_bounds__(kXThreads, 2)
+template <bool kF32, bool kPipe, int kT = kXThreads, int kB = 2, int kUnroll = 1>
+__global__ void __launch_bounds__(kT, kB)
 wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupArgs A, double* __restrict__ out_dE,
                    double* __restrict__ out_kick, unsigned long long* counters, const PeerOut peers) {
     constexpr int VB = kF32 ? DFCSR_VOXEL_FLOATS * 4 : DFCSR_VOXEL_DOUBLES * 8;   // bytes per voxel
     __shared__ XGroupShared sh;
-    extern __shared__ double2 node_tab2[];                 // [nreg * nzp + 1][kXRec] doubles, 16-byte aligned records
+    // dynamic shared memory: one 2 x kXWin window of 48-byte transverse-blended history nodes per warp, then the node
+    // table [nreg * nzp + 1][kXRec] (16-byte aligned records)
+    extern __shared__ double2 xg_smem[];
+    double2* const node_tab2 = xg_smem + (kT / 32) * (2 * kXWin * 3);
     double* const node_tab = reinterpret_cast<double*>(node_tab2);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -169,8 +182,10 @@ wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupA
     const bool lane_valid = ix < M.mx.n;
     const int nz = wp.nz;
     const int nzp = (nz + 31) & ~31;
-    // behind the node table: one 2 x kXWin window of 48-byte transverse-blended nodes per warp
-    double* const tile = node_tab + (size_t)kXRec * (3 * nzp + 1) + (size_t)warp * (2 * kXWin * 6);
+    // the warp's window as a 32-bit shared-space address, accessed through ld/st.shared below (a generic pointer would be
+    // re-derived from the thread and CTA ids at every step once registers are short)
+    unsigned tile_s = (unsigned)__cvta_generic_to_shared(reinterpret_cast<double*>(xg_smem) + warp * (2 * kXWin * 6));
+    asm volatile("mov.u32 %0, %0;" : "+r"(tile_s));        // opaque: keep it in a register instead of recomputing it
 
     // ---- set-up 1: the group's s, its rectangles and the list of pruned x' nodes ---------------------
     const double zz = axis_node(M.mz, iz);
@@ -279,15 +294,18 @@ wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupA
                 r2 = add_rn(mul_rn(rx, rx), mul_rn(ry, ry));
                 return sqrt_pair_fast(r2, rr, ir);
             };
-            // exceptional exponents (r = 0, inf, NaN: library path), then the fractional cell coordinates
-            auto locate = [&](const double2* q, bool fast, double r2, double rr, double& ir, double& ut, double& uz) {
-                if (!fast) {
-                    ir = rsqrt(r2);
-                    rr = __dsqrt_rn(r2);
-                }
+            // fractional cell coordinates of the retarded point (CSR.py:648-650, interp3D.py:30-36)
+            auto locate = [&](const double2* q, double rr, double& ut, double& uz) {
                 const double t_ret = Pt - rr;
                 ut = (t_ret - H.min_t) * H.inv_dt;
                 uz = ((q[3].y - t_ret) - H.min_z) * H.inv_dz;
+            };
+            // exceptional exponents (r = 0, inf, NaN): the library's sqrt / rsqrt instead of the fused fast path
+            auto fixup = [&](const double2* q, bool fast, double r2, double& ir, double& ut, double& uz) {
+                if (!fast) {
+                    ir = rsqrt(r2);
+                    locate(q, __dsqrt_rn(r2), ut, uz);
+                }
             };
             // The five fields at (ut, uz).  All lanes of a step look at nearly the same place of the (t', z) plane (same x'
             // and s' node, observation points 0.1 sigma_x apart), and the place moves slowly along the sweep: the warp keeps
@@ -320,10 +338,9 @@ wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupA
                         double y[5];
                         yblend_node<kF32>(row0 + o, row1 + o, wy0, yd, y);
                         __syncwarp();
-                        double2* dst = reinterpret_cast<double2*>(tile + lane * 6);
-                        dst[0] = make_double2(y[0], y[1]);
-                        dst[1] = make_double2(y[2], y[3]);
-                        tile[lane * 6 + 4] = y[4];
+                        sts128(tile_s + lane * 48, y[0], y[1]);
+                        sts128(tile_s + lane * 48 + 16, y[2], y[3]);
+                        sts64(tile_s + lane * 48 + 32, y[4]);
                         __syncwarp();
                         inwin = ok;
                     }
@@ -332,15 +349,11 @@ wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupA
                 const double w00 = wt0 * wz0, w01 = wt0 * zd, w10 = td * wz0, w11 = td * zd;
                 double Y[4][5];
                 if (inwin || !ok) {
-                    const double* p = tile + (inwin ? (z0 - zw) * 6 : 0);
-                    const double2 a0 = *reinterpret_cast<const double2*>(p), a1 = *reinterpret_cast<const double2*>(p + 2);
-                    const double2 b0 = *reinterpret_cast<const double2*>(p + 6), b1 = *reinterpret_cast<const double2*>(p + 8);
-                    const double2 c0 = *reinterpret_cast<const double2*>(p + 96), c1 = *reinterpret_cast<const double2*>(p + 98);
-                    const double2 d0 = *reinterpret_cast<const double2*>(p + 102), d1 = *reinterpret_cast<const double2*>(p + 104);
-                    Y[0][0] = a0.x; Y[0][1] = a0.y; Y[0][2] = a1.x; Y[0][3] = a1.y; Y[0][4] = p[4];
-                    Y[1][0] = b0.x; Y[1][1] = b0.y; Y[1][2] = b1.x; Y[1][3] = b1.y; Y[1][4] = p[10];
-                    Y[2][0] = c0.x; Y[2][1] = c0.y; Y[2][2] = c1.x; Y[2][3] = c1.y; Y[2][4] = p[100];
-                    Y[3][0] = d0.x; Y[3][1] = d0.y; Y[3][2] = d1.x; Y[3][3] = d1.y; Y[3][4] = p[106];
+                    const unsigned p = tile_s + (inwin ? (unsigned)(z0 - zw) * 48u : 0u);
+                    lds128(p, Y[0][0], Y[0][1]);           lds128(p + 16, Y[0][2], Y[0][3]);           lds64(p + 32, Y[0][4]);
+                    lds128(p + 48, Y[1][0], Y[1][1]);      lds128(p + 64, Y[1][2], Y[1][3]);           lds64(p + 80, Y[1][4]);
+                    lds128(p + 768, Y[2][0], Y[2][1]);     lds128(p + 784, Y[2][2], Y[2][3]);          lds64(p + 800, Y[2][4]);
+                    lds128(p + 816, Y[3][0], Y[3][1]);     lds128(p + 832, Y[3][2], Y[3][3]);          lds64(p + 848, Y[3][4]);
                 } else {
                     int s0 = H.head + t0;
                     s0 -= (s0 >= H.cap) ? H.cap : 0;
@@ -406,16 +419,21 @@ wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupA
                 // independent of it; the gather of j + 1 (the only divergent part) follows.
                 double rx, ry, r2, rr, ir, ut, uz, fld[5];
                 bool fast = geometry(rec, rx, ry, r2, rr, ir);
-                locate(rec, fast, r2, rr, ir, ut, uz);
+                locate(rec, rr, ut, uz);
+                fixup(rec, fast, r2, ir, ut, uz);
                 bool ok = in_grid(ut, uz);
                 n_node += (unsigned)__popc(__ballot_sync(0xffffffffu, ok));
                 new_scale(rec[3].x);
                 gather(ut, uz, ok, fld);
+#pragma unroll kUnroll
                 for (int j = j_lo; j <= j_hi; ++j, rec += kXRec / 2) {
                     double rxn, ryn, irn;
-                    fast = geometry(rec + kXRec / 2, rxn, ryn, r2, rr, irn);   // node j + 1 (the table is padded by one record)
-                    algebra(rec, fld, rx, ry, ir, ok);                         // node j
-                    locate(rec + kXRec / 2, fast, r2, rr, irn, ut, uz);
+                    // one straight-line block: the dependent chain of node j + 1 (the table is padded by one record)
+                    // next to the independent algebra of node j
+                    fast = geometry(rec + kXRec / 2, rxn, ryn, r2, rr, irn);
+                    locate(rec + kXRec / 2, rr, ut, uz);
+                    algebra(rec, fld, rx, ry, ir, ok);
+                    fixup(rec + kXRec / 2, fast, r2, irn, ut, uz);
                     ok = in_grid(ut, uz) && (j < j_hi);
                     n_node += (unsigned)__popc(__ballot_sync(0xffffffffu, ok));
                     new_scale(rec[kXRec / 2 + 3].x);
@@ -426,7 +444,8 @@ wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupA
                 for (int j = j_lo; j <= j_hi; ++j, rec += kXRec / 2) {
                     double rx, ry, r2, rr, ir, ut, uz, fld[5];
                     const bool fast = geometry(rec, rx, ry, r2, rr, ir);
-                    locate(rec, fast, r2, rr, ir, ut, uz);
+                    locate(rec, rr, ut, uz);
+                    fixup(rec, fast, r2, ir, ut, uz);
                     const bool ok = in_grid(ut, uz);
                     const unsigned okm = __ballot_sync(0xffffffffu, ok);
                     if (okm == 0u) continue;
