@@ -434,11 +434,17 @@ def gpu_arm(args):
     k4_bytes = (320.0 if args.precision == "fp64" else 160.0) * n_gat_local
     traffic = None                      # DRAM bytes per K4 launch from the committed ncu --set full capture
     traffic_src = None
+    ncu_pipes = {}
+    mapping = getattr(csr, "last_wake_mapping", "point")
+    k4_name = ("wake_xgroup_kernel (K4, one lane per observation point of a mesh row)" if mapping == "xgroup"
+               else "wake_mesh_kernel_p (K4, one CTA per observation point)")
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "k4_ncu_traffic.json")))
+        tr = tr.get(mapping, tr)        # one record per K4 mapping ("xgroup" / "point")
         if args.precision == "fp64":
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
             traffic_src = tr.get("source")
+            ncu_pipes = {k: tr[k] for k in ("fp64_pipe_pct", "l1_data_pipe_pct", "issue_active_pct", "kernel") if k in tr}
     except Exception:
         pass
     achieved = k4_bytes / (k4_ms * 1e-3) / 1e9
@@ -458,13 +464,14 @@ def gpu_arm(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "s_per_lattice_step": ms_step * 1e-3,
         "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl_name, "mesh": mesh_now,
+        "config": {"workload": wl_name, "mesh": mesh_now, "k4_mapping": mapping,
                    "integration": [wp.nx, wp.nz], "n_particle": wl["n_particle"],
                    "history": list(hot_state["hist"].shape),
                    "samples_per_point": spp, "position_m": wl["position"],
                    "l2": "256 MiB device memset between steps (inside the timed region)",
                    "points_per_gpu": n_pts // world,
-                   "parallelism": (f"obs-mesh block split x{world} (4096 points per GPU), " +
+                   "parallelism": ((f"obs-mesh x-groups (32 points of a mesh row) dealt out round-robin x{world} (4096 points per GPU), "
+                                    if mapping == "xgroup" else f"obs-mesh block split x{world} (4096 points per GPU), ") +
                                    ("exchange fused into K4 (NVLink peer-memory stores + one barrier)"
                                     if getattr(csr, "_peer_grid", None) is not None else "NCCL all-gather") +
                                    (f"; particles sharded x{world} (statistics tables + integer deposit grids combined over "
@@ -483,7 +490,7 @@ def gpu_arm(args):
                 "d2h_bytes_per_step_rank0": int(out_host[0].numel() * 8 * 2 + out_host[2].numel() * 8)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "l1", "kernel": "wake_mesh_kernel_p (K4)", "achieved": achieved, "peak": l1_peak,
+        "roofline": {"bound": "l1", "kernel": k4_name, "achieved": achieved, "peak": l1_peak,
                      "unit": "GB/s", "frac": achieved / l1_peak, "traffic": traffic,
                      "peak_source": l1_src, "traffic_source": traffic_src,
                      "hbm_actual": {"frac": (traffic / (k4_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None, "peak": hbm_peak,
@@ -493,10 +500,13 @@ def gpu_arm(args):
                      "k4_ms_per_launch": k4_ms, "k4_share_of_step": k4_ms / ms_step,
                      "in_grid_samples_per_launch": n_in_local, "in_grid_fraction": n_in_local / (n_pts * spp / world),
                      "gathered_samples_per_launch": n_gat_local,
+                     "ncu": ncu_pipes,
                      "note": "achieved = algorithmic gather bytes (320 B per in-grid integrand sample that is actually gathered; "
                              "samples whose eight voxels carry no density are skipped via the row-support table and count 0 B) / "
-                             "K4 launch time; this traffic is served by L1/L2, so the roofline is the L1 load path, not HBM "
-                             "(DESIGN.md §4, profiles/)"},
+                             "K4 launch time; this traffic never reaches HBM (the history stack is L2-resident), so the roofline "
+                             "is the L1 -> register load path.  The point kernel moves every one of these bytes through that "
+                             "path; the x-group kernel serves a sample's four transverse-blended corners (160 B) from a per-warp "
+                             "shared-memory window and is bound by the fp64 pipe instead (roofline.ncu, DESIGN.md section 4)"},
         "parity": hot_state["parity"],
     }
     if strong is not None:
@@ -602,19 +612,20 @@ def strong_scaling_record(world, steps, flush):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         grids = torch.stack([csr.dE_dct, csr.x_kick]).clone()
         shards = csr.beam.shards.mode if csr.beam.shards is not None else None
+        mapping = getattr(csr, "last_wake_mapping", "point")
         del csr
         torch.cuda.empty_cache()
-        return float(ms[0]), float(ms[1]), grids, shards
+        return float(ms[0]), float(ms[1]), grids, (shards, mapping)
 
-    t1, k41, g1, _ = measure(False)
+    t1, k41, g1, (_, mapping1) = measure(False)
     rec = {"workload": STRONG["name"], "mesh": [STRONG["mesh"]["xbins"], STRONG["mesh"]["zbins"]],
            "n_particle": STRONG["beam"]["n_particle"], "steps": steps, "t_1_ms": t1, "k4_1_ms": k41,
-           "non_k4_1_ms": t1 - k41,
+           "non_k4_1_ms": t1 - k41, "k4_mapping": mapping1,
            "how": "full step (statistics, K1, K2, K3, K4 + exchange, K5, statistics) with the particles resident, L2 flushed "
                   "between steps, CUDA events, max over ranks; t_1 = every rank alone with all particles and the whole mesh, "
                   "measured in the same processes"}
     if world > 1:
-        tn, k4n, gn, shards = measure(True)
+        tn, k4n, gn, (shards, _) = measure(True)
         rec.update({"n_gpus": world, "t_N_ms": tn, "k4_N_ms": k4n, "non_k4_N_ms": tn - k4n, "speedup": t1 / tn,
                     "efficiency": t1 / (world * tn), "particles": f"sharded ({shards})" if shards else "replicated",
                     "grids_bitwise_equal_to_single_gpu": bool(torch.equal(gn, g1))})

@@ -298,7 +298,8 @@ int dfcsr_wake_grid_peers(const dfcsr_history* hist, const dfcsr_lattice* lat, c
  * ~1e-15 relative, both within 1e-10 of the reference) and is a function of the plan only: any split of the groups over
  * launches / ranks gives bitwise the same grid.
  * dfcsr_wake_xgroup_plan: n_groups = 0 when the mapping does not apply to this step (chirp band, a sparse grid that
- * dfcsr_wake_uses_skipping would serve, fewer than 70 % of the lanes carrying a point, integration zbins too large);
+ * dfcsr_wake_uses_skipping would serve, fewer than 70 % of the lanes carrying a point, a bunch so compressed that the
+ * points of a group look at history cells dozens of cells apart, integration zbins too large);
  * the plan depends on the history geometry, the beam scalars and the WHOLE mesh, never on the split. */
 typedef struct dfcsr_xgroup_plan {
     int64_t n_groups;                  /* groups of the whole mesh; 0 = use dfcsr_wake_grid                     */

@@ -21,6 +21,8 @@ inp = bench._input_dict(wl)
 tilt = os.environ.get("DFCSR_TILT")
 if tilt:
     inp["input_beam"]["tilt"] = float(tilt)
+if os.environ.get("DFCSR_SIGMA_Z"):               # a shorter bunch: the lanes of an x-group spread over more history cells
+    inp["input_beam"]["sigma_z"] = float(os.environ["DFCSR_SIGMA_Z"])
 mesh = os.environ.get("DFCSR_MESH")
 if mesh:
     xb, zb = (int(v) for v in mesh.split("x"))
@@ -28,7 +30,7 @@ if mesh:
 csr = CSR2D(inp, parallel=False, verbose=False, precision=os.environ.get("DFCSR_PRECISION", "fp64"))
 csr.run(stop_time=wl["position"] - 0.05)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=csr.device)
-print(f"# K4 mappings on the bench workload, tilt={tilt or 0}, precision={os.environ.get('DFCSR_PRECISION', 'fp64')}, "
+print(f"# K4 mappings on the bench workload, sigma_z={os.environ.get('DFCSR_SIGMA_Z', 'default')}, tilt={tilt or 0}, precision={os.environ.get('DFCSR_PRECISION', 'fp64')}, "
       f"mesh {csr.CSR_params.xbins}x{csr.CSR_params.zbins}, slope {float(csr.beam._slope[0]):.3f}")
 res = {}
 for mapping in ("point", "auto"):
