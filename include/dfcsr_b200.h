@@ -322,6 +322,10 @@ int dfcsr_wake_grid_xgroups(const dfcsr_history* hist, const dfcsr_lattice* lat,
                             const uint64_t* h_peer_grids, int32_t n_peers, void* d_workspace, int64_t workspace_bytes,
                             unsigned long long* d_counters, void* stream);
 
+/* Loads the code of the wake kernels now instead of at their first launch (CUDA loads kernels lazily; the two large ones
+ * cost tens of milliseconds, which would otherwise land in the first lattice step).  Needs a current CUDA context. */
+int dfcsr_wake_preload(void);
+
 /* 1 if the wake launches above would use zero-density skipping for this history and these beam scalars (row-support
  * table present and the grid sparse by construction: |slope0| > 1, the chirp-band branch of CSR.py:480, or a history
  * grid more than 1.5x the +-5 sigma box of the current bunch; wp->skip_mode ON / OFF overrides), else 0; < 0 on error. */

@@ -106,6 +106,7 @@ SIGNATURES = {
     "dfcsr_wake_xgroup_plan": (C.c_int, [C.POINTER(History), C.POINTER(WakeParams), Axis, Axis, C.POINTER(XGroupPlan)]),
     "dfcsr_wake_grid_xgroups": (C.c_int, [C.POINTER(History), C.POINTER(Lattice), C.POINTER(WakeParams), Axis, Axis, _D, _D,
                                           _L, _L, _L, _P, _P, C.POINTER(C.c_uint64), _I, _P, _L, _P, _P]),
+    "dfcsr_wake_preload": (C.c_int, []),
     "dfcsr_wake_uses_skipping": (C.c_int, [C.POINTER(History), C.POINTER(WakeParams)]),
     "dfcsr_wake_point_debug": (C.c_int, [C.POINTER(History), C.POINTER(Lattice), C.POINTER(WakeParams),
                                          _D, _D, _P, _P, _L, _P, _P, _P]),

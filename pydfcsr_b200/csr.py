@@ -70,6 +70,8 @@ class CSR2D:
             device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)) if self.parallel else torch.cuda.current_device())
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
+        torch.zeros(1, device=self.device)                       # make sure the device has a context
+        _lib.check(_lib.lib.dfcsr_wake_preload(), "dfcsr_wake_preload")   # kernel code is loaded now, not in the first step
         if input_file is not None:
             self.parse_input(input_file)
             self.input_file = input_file

@@ -39,7 +39,10 @@ def build(name):
            "CSR_computation": dict(compute_CSR=1, apply_CSR=0, transverse_on=1, write_beam=None, write_wakes=False,
                                    workdir="/tmp/dfcsr_cfg", xbins=mesh[0], zbins=mesh[1], xlim=5, zlim=5)}
     from pydfcsr_b200 import CSR2D
-    return CSR2D(inp, parallel=False, verbose=False, precision=os.environ.get("DFCSR_PRECISION", "fp64")), stop
+    csr = CSR2D(inp, parallel=False, verbose=False, precision=os.environ.get("DFCSR_PRECISION", "fp64"))
+    if os.environ.get("DFCSR_SKIP"):                 # developer runs: force the zero-density skipping policy
+        csr.skip_mode = os.environ["DFCSR_SKIP"]
+    return csr, stop
 
 
 def oracle_points(csr, picks):

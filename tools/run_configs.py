@@ -68,6 +68,7 @@ def main(names):
         e_k = np.max(np.abs(kick[picks] - ref[:, 1])) / np.max(np.abs(kick))
         T = len(trk.time_interp)
         shape = (T, len(trk.x_grid_interp), len(trk.z_grid_interp))
+        name = f"{name}[{getattr(csr, 'last_wake_mapping', 'point')[0]}]"          # [x] = x-group mapping, [p] = point kernel
         print(f"{name:14s} {beam.x.numel():10d} {csr.CSR_params.xbins:4d}x{csr.CSR_params.zbins:<4d} {str(shape):>18s} "
               f"{step_ms:9.3f} {k4_ms:9.3f} {rate:>10s} {in_grid:>8s} {e_de:11.2e} {e_k:11.2e}   (setup run {setup:.1f} s)",
               flush=True)
