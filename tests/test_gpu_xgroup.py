@@ -167,3 +167,32 @@ def test_csr2d_selects_the_mapping_per_step(dev):
     assert float((a[0] - csr.dE_dct).abs().max() / csr.dE_dct.abs().max()) < 1e-12
     assert float((a[1] - csr.x_kick).abs().max() / csr.x_kick.abs().max()) < 1e-12
     assert float(a[0].abs().max()) > 0
+
+
+@pytest.mark.parametrize("T,zstep,xstep", [(1, 1, 1), (2, 40, 1), (3, 64, 50)])
+def test_xgroup_small_histories(dev, T, zstep, xstep):
+    """Single-slice windows (the slice pair is the same slice twice), z grids shorter than the warp's 16-node window and
+    x grids of a few rows: the window clamps, the clamp cells and the extrapolation band keep the reference's rules
+    (interp3D.py:30-64).  Oracle parity on a coarsened copy of the scenario's history."""
+    import torch
+    from pydfcsr_b200 import ops
+    sc = scenario.chicane_entry(tilt=0.0)
+    st, lat = sc["stack"], sc["lattice"]
+    data = {k: np.ascontiguousarray(st.data[k][-T:, ::xstep, ::zstep]) for k in O.FIELDS}
+    small = O.HistoryStack(data, st.min_x + (st.shape[0] - T) * st.delta_x, st.min_y, st.min_z,
+                           st.delta_x, st.delta_y * xstep, st.delta_z * zstep)
+    assert small.shape[0] == T and (zstep == 1 or small.shape[2] < 16)
+    hist = ops.DeviceHistory.from_stacks([small.data[k] for k in O.FIELDS], small.min_x, small.min_y, small.min_z,
+                                         small.delta_x, small.delta_y, small.delta_z, dev, cap=T + 2, head=1)
+    dlat = ops.DeviceLattice.upload(lat.coords, lat.n_vec, lat.tau_vec, lat.rho, lat.distance, lat.min_s, lat.delta_s, dev)
+    nx, nz = 36, 40
+    wp = ops.wake_params(nx=nx, nz=nz, skip="off", **sc["wake_scalars"])
+    osc = O.WakeScalars(nx=nx, nz=nz, **sc["wake_scalars"])
+    xm, zm, xa, za, slope, icpt = _mesh(sc, 32, 3)
+    plan = ops.wake_xgroup_plan(hist, wp, xa, za)
+    if plan.n_groups == 0:
+        pytest.skip("the plan sends this history to the point kernel (spread criterion)")
+    de, kick = ops.wake_grid_xgroups(hist, dlat, wp, xa, za, slope, icpt, plan=plan)
+    ref_de, ref_kick = O.wake_mesh(xm, zm, osc, lat, small)
+    assert float(np.abs(ref_de).max()) > 0
+    assert _rel(de.cpu().numpy(), ref_de) < TOL and _rel(kick.cpu().numpy(), ref_kick) < TOL
