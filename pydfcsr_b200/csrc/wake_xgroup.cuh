@@ -242,6 +242,7 @@ wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupA
     const int nunits = (total_nodes + U - 1) / U;
     double* const gpart = A.partials + (size_t)gl * A.max_units * 64;
     unsigned long long n_in = 0;
+    const bool counting = counters != nullptr;      // sample accounting is optional (bench / tests)
     const int Zm1 = H.Z - 1, Tm1 = H.T - 1;
 
     unsigned int* const q_next = A.tickets + 2 * gl;
@@ -422,7 +423,7 @@ wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupA
                 locate(rec, rr, ut, uz);
                 fixup(rec, fast, r2, ir, ut, uz);
                 bool ok = in_grid(ut, uz);
-                n_node += (unsigned)__popc(__ballot_sync(0xffffffffu, ok));
+                if (counting) n_node += (unsigned)__popc(__ballot_sync(0xffffffffu, ok));
                 new_scale(rec[3].x);
                 gather(ut, uz, ok, fld);
 #pragma unroll kUnroll
@@ -435,7 +436,7 @@ wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupA
                     algebra(rec, fld, rx, ry, ir, ok);
                     fixup(rec + kXRec / 2, fast, r2, irn, ut, uz);
                     ok = in_grid(ut, uz) && (j < j_hi);
-                    n_node += (unsigned)__popc(__ballot_sync(0xffffffffu, ok));
+                    if (counting) n_node += (unsigned)__popc(__ballot_sync(0xffffffffu, ok));
                     new_scale(rec[kXRec / 2 + 3].x);
                     gather(ut, uz, ok, fld);
                     rx = rxn; ry = ryn; ir = irn;
