@@ -336,6 +336,7 @@ class CSR2D:
     def _xgroup_plan(self, wp):
         """The x-group plan of this step, or None when the point kernel serves it (dfcsr_wake_xgroup_plan)."""
         if self.wake_mapping == "point":
+            self.last_wake_mapping = "point"
             return None
         xa, za = self._mesh_axes
         plan = ops.wake_xgroup_plan(self.DF_tracker.history, wp, xa, za)
