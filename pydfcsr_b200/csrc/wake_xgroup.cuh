@@ -140,6 +140,36 @@ __device__ __forceinline__ void yblend_node(const char* __restrict__ pa, const c
     }
 }
 
+// Moves the warp's 2 x kXWin window of transverse-blended history nodes so that it holds the cells (t0, z0) of all lanes
+// with `ok` -- if they fit one window (same slice pair, z spread <= kXWin - 2) -- and refills it: lane -> (slice tw or its
+// successor, node zw + 0..15), clamped into the grid (clamped copies are never read: a valid cell ends at node Z - 1).
+// Returns (tw << 32) | zw, or -1 when the lanes do not fit (they then gather from global memory).  Warp-uniform.
+template <bool kF32>
+__device__ __noinline__ long long xg_move_window(int HT, int HZ, int Hhead, int Hcap, bool ok, int t0, int z0, const char* row0,
+                                                 const char* row1, double wy0, double yd, unsigned tile_s, unsigned slice_bytes) {
+    constexpr int VB = kF32 ? DFCSR_VOXEL_FLOATS * 4 : DFCSR_VOXEL_DOUBLES * 8;
+    const int lane = threadIdx.x & 31;
+    const int zmin = __reduce_min_sync(0xffffffffu, ok ? z0 : INT_MAX);
+    const int zmax = __reduce_max_sync(0xffffffffu, ok ? z0 : INT_MIN);
+    const int tmin = __reduce_min_sync(0xffffffffu, ok ? t0 : INT_MAX);
+    const int tmax = __reduce_max_sync(0xffffffffu, ok ? t0 : INT_MIN);
+    if (tmin != tmax || zmax - zmin > kXWin - 2) return -1;
+    const int tw = tmin;
+    const int zw = max(0, min(zmin - ((kXWin - 2 - (zmax - zmin)) >> 1), HZ - kXWin));
+    const int ti = lane >> 4, zn = min(zw + (lane & (kXWin - 1)), HZ - 1);
+    int sl = Hhead + ((ti && tw != HT - 1) ? tw + 1 : tw);
+    sl -= (sl >= Hcap) ? Hcap : 0;
+    const size_t o = (size_t)((unsigned long long)(unsigned)sl * slice_bytes + (unsigned)zn * (unsigned)VB);
+    double y[5];
+    yblend_node<kF32>(row0 + o, row1 + o, wy0, yd, y);
+    __syncwarp();
+    sts128(tile_s + lane * 48, y[0], y[1]);
+    sts128(tile_s + lane * 48 + 16, y[2], y[3]);
+    sts64(tile_s + lane * 48 + 32, y[4]);
+    __syncwarp();
+    return ((long long)tw << 32) | (long long)(unsigned)zw;
+}
+
 // the two results of the group's points (CSR.py:588-589), x-major flattening of the mesh (CSR.py:382-389)
 __device__ __forceinline__ void xgroup_store(const MeshSrc& M, const dfcsr_wake_params& wp, const PeerOut& peers,
                                              double* out_dE, double* out_kick, int ix, int iz, bool lane_valid,
@@ -323,26 +353,11 @@ wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupA
                 if (z0 == Zm1) { z0 = Zm1 - 1; zd = 1.0; }      // clamp cell: same voxel, weight exactly 1
                 bool inwin = (t0 == tw) && ((unsigned)(z0 - zw) <= (unsigned)(kXWin - 2));
                 if (__any_sync(0xffffffffu, ok && !inwin)) {
-                    const int zmin = __reduce_min_sync(0xffffffffu, ok ? z0 : INT_MAX);
-                    const int zmax = __reduce_max_sync(0xffffffffu, ok ? z0 : INT_MIN);
-                    const int tmin = __reduce_min_sync(0xffffffffu, ok ? t0 : INT_MAX);
-                    const int tmax = __reduce_max_sync(0xffffffffu, ok ? t0 : INT_MIN);
-                    if (tmin == tmax && zmax - zmin <= kXWin - 2) {
-                        tw = tmin;
-                        zw = max(0, min(zmin - ((kXWin - 2 - (zmax - zmin)) >> 1), H.Z - kXWin));
-                        // lane -> (slice tw or its successor, node zw + 0..15), clamped into the grid (clamped copies are
-                        // never read: a valid cell ends at node Z - 1)
-                        const int ti = lane >> 4, zn = min(zw + (lane & (kXWin - 1)), Zm1);
-                        int sl = H.head + ((ti && tw != Tm1) ? tw + 1 : tw);
-                        sl -= (sl >= H.cap) ? H.cap : 0;
-                        const size_t o = (size_t)((unsigned long long)(unsigned)sl * slice_bytes + (unsigned)zn * (unsigned)VB);
-                        double y[5];
-                        yblend_node<kF32>(row0 + o, row1 + o, wy0, yd, y);
-                        __syncwarp();
-                        sts128(tile_s + lane * 48, y[0], y[1]);
-                        sts128(tile_s + lane * 48 + 16, y[2], y[3]);
-                        sts64(tile_s + lane * 48 + 32, y[4]);
-                        __syncwarp();
+                    // rare (a window lasts ~25-80 steps): kept out of line so that none of it is hoisted into the step
+                    const long long moved = xg_move_window<kF32>(H.T, H.Z, H.head, H.cap, ok, t0, z0, row0, row1, wy0, yd, tile_s, slice_bytes);
+                    if (moved >= 0) {
+                        tw = (int)(moved >> 32);
+                        zw = (int)(moved & 0xffffffffll);
                         inwin = ok;
                     }
                 }

@@ -29,6 +29,8 @@ inp = {"input_beam": {"style": "synthetic", "n_particle": n_particle, "seed": 0}
        "CSR_computation": dict(compute_CSR=1, apply_CSR=1, transverse_on=1, write_beam=None, write_wakes=False,
                                workdir="/tmp/dfcsr_profile", xbins=mx, zbins=mz, xlim=5, zlim=5)}
 csr = CSR2D(inp, parallel=parallel, verbose=False)
+if os.environ.get("DFCSR_SKIP"):                       # force the zero-density skipping policy (auto / on / off)
+    csr.skip_mode = os.environ["DFCSR_SKIP"]
 rank, world = (csr.rank, csr.world_size) if parallel else (0, 1)
 counters = torch.zeros(3, dtype=torch.int64, device=csr.device)
 csr.wake_counters = counters
@@ -44,7 +46,7 @@ def timed():
     b.record()
     trk = csr.DF_tracker
     log.append((csr.beam.position, float(csr.beam._slope[0]), len(trk.time_interp), len(trk.x_grid_interp),
-                len(trk.z_grid_interp), a, b, before, counters.clone()))
+                len(trk.z_grid_interp), a, b, before, counters.clone(), getattr(csr, "last_wake_mapping", "point")[0]))
 
 
 if parallel:
@@ -61,15 +63,18 @@ csr.run()
 torch.cuda.synchronize()
 wall = time.perf_counter() - t0
 if rank == 0:
-    k4 = np.array([a.elapsed_time(b) for (_, _, _, _, _, a, b, _, _) in log])
-    full = np.array([int((after - before)[1]) for (*_, before, after) in log], dtype=np.float64) * world   # whole mesh
+    k4 = np.array([rec[5].elapsed_time(rec[6]) for rec in log])
+    full = np.array([int((rec[8] - rec[7])[1]) for rec in log], dtype=np.float64) * world   # whole mesh
     print(f"# full chicane, {n_particle} particles, {mx}x{mz} mesh, 200x200 integration, {world} GPU(s): "
           f"{len(log)} wake steps in {wall:.3f} s wall ({wall / len(log) * 1e3:.2f} ms per lattice step), "
           f"wake kernel + gather {k4.sum() * 1e-3:.3f} s, history rebuilds {csr.DF_tracker.rebuilds}")
     print(f"# samples the reference would evaluate: {full.sum():.3e}  =>  {full.sum() / wall:.3e} samples/s over the whole run")
-    print(f"{'s [m]':>7s} {'slope':>8s} {'T':>3s} {'X':>5s} {'Z':>5s} {'wake ms':>8s} {'samples/s':>10s}")
+    print(f"{'s [m]':>7s} {'slope':>8s} {'T':>3s} {'X':>5s} {'Z':>5s} {'wake ms':>8s} {'samples/s':>10s}  K4 mapping (x = x-groups, p = point)")
     for i in list(range(0, len(log), 6)) + [len(log) - 1]:
         pos, slope, T, X, Z = log[i][:5]
-        print(f"{pos:7.2f} {slope:8.2f} {T:3d} {X:5d} {Z:5d} {k4[i]:8.3f} {full[i] / (k4[i] * 1e-3):10.3e}")
+        print(f"{pos:7.2f} {slope:8.2f} {T:3d} {X:5d} {Z:5d} {k4[i]:8.3f} {full[i] / (k4[i] * 1e-3):10.3e}  {log[i][9]}")
+    nx_steps = sum(1 for rec in log if rec[9] == "x")
+    print(f"# steps on the x-group mapping: {nx_steps} of {len(log)}; wake ms on them {sum(k for k, rec in zip(k4, log) if rec[9] == 'x'):.1f}, "
+          f"on the point kernel {sum(k for k, rec in zip(k4, log) if rec[9] == 'p'):.1f}")
 if parallel:
     torch.distributed.destroy_process_group()
