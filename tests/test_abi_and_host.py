@@ -116,6 +116,19 @@ for n in (7, 10, 4096):
     send[:, :count[rank]] = torch.from_numpy(full[:, displ[rank]:displ[rank] + count[rank]])
     got = D.all_gather_blocks(send, count, n).numpy()
     assert np.array_equal(got, full), (rank, n)
+# x-groups dealt out round-robin (group = iz * ceil(nx/32) + ix // 32, rank = group % world): every rank fills its own
+# points of a full grid; the exchange copies every point from its owner (-0.0 stays -0.0, NaN placeholders never leak)
+for nx, nz in ((32, 5), (48, 7), (70, 3)):
+    n = nx * nz
+    owner = D.xgroup_owner(nx, nz, world, torch.device("cpu"))
+    ix, iz = np.divmod(np.arange(n), nz)
+    assert np.array_equal(owner.numpy(), (iz * ((nx + 31) // 32) + ix // 32) % world)
+    full = -np.arange(2 * n, dtype=np.float64).reshape(2, n)          # element 0 is -0.0
+    mine = torch.full((2, n), float("nan"), dtype=torch.float64)
+    sel = (owner == rank)
+    mine[:, sel] = torch.from_numpy(full)[:, sel]
+    got = D.all_gather_select(mine, owner).numpy()
+    assert np.array_equal(got, full) and np.signbit(got[0, 0]), (rank, nx, nz)
 # the fused K4 exchange needs NCCL ranks with CUDA peer mappings: on gloo/CPU the collective decision is "NCCL path"
 assert D.make_peer_wake_grid(4096, torch.device("cpu")) is None
 # particle shards (host logic; the kernels are covered on the GPU): whole chunks per rank, exact cover, gather restores
