@@ -291,7 +291,8 @@ int dfcsr_wake_grid_peers(const dfcsr_history* hist, const dfcsr_lattice* lat, c
 /* ---- K4, x-group mapping (csrc/wake_xgroup.cuh): same get_CSR_wake results (CSR.py:454-602), other work split ------
  * Without chirp band (|slope0| <= 1, CSR.py:480) the (x', s') quadrature nodes of an observation point depend on its s
  * only, and the mesh of get_CSR_mesh is a tensor grid (CSR.py:380-389): all points of one z row share their nodes.  A
- * GROUP is up to 32 mesh points with the same z index and consecutive x indices (global group g = iz * ceil(nx/32) + gx);
+ * GROUP is up to plan.group_points (32) mesh points with the same z index and consecutive x indices (global group
+ * g = iz * ceil(nx / group_points) + gx);
  * the kernel gives every point of a group one warp lane, walks the s' nodes in sequence and keeps the transverse-blended
  * corners of each lane's history cell in registers, so most samples need no history load at all (1.3-1.5x faster than
  * the point kernel on a bunch that fills its grid).  The summation order differs from dfcsr_wake_grid (results agree to
@@ -306,6 +307,8 @@ typedef struct dfcsr_xgroup_plan {
     int32_t unit_nodes;                /* x' nodes per partial sum (fixes the summation order)                  */
     int32_t max_units;                 /* partial sums per group                                                */
     int64_t workspace_bytes_per_group; /* d_workspace of a launch must hold group_count times this              */
+    int32_t group_points;              /* mesh points per group (32: one per lane of a warp)                    */
+    int32_t reserved;                  /* 0                                                                     */
 } dfcsr_xgroup_plan;
 
 int dfcsr_wake_xgroup_plan(const dfcsr_history* hist, const dfcsr_wake_params* wp, dfcsr_axis x_axis, dfcsr_axis z_axis,

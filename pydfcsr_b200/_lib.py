@@ -62,7 +62,7 @@ class WakeParams(C.Structure):
 
 class XGroupPlan(C.Structure):
     _fields_ = [("n_groups", C.c_int64), ("unit_nodes", C.c_int32), ("max_units", C.c_int32),
-                ("workspace_bytes_per_group", C.c_int64)]
+                ("workspace_bytes_per_group", C.c_int64), ("group_points", C.c_int32), ("reserved", C.c_int32)]
 
 
 _P = C.c_void_p

@@ -387,9 +387,10 @@ class CSR2D:
                 ops.wake_grid_xgroups(self.DF_tracker.history, lat, wp, xa, za, *self._mesh_slope, plan=plan,
                                       group_first=self.rank, group_stride=self.world_size, out=mine,
                                       counters=getattr(self, "wake_counters", None))
-                key = (p.xbins, p.zbins)
+                key = (p.xbins, p.zbins, plan.group_points)
                 if getattr(self, "_xgroup_owner_key", None) != key:
-                    self._xgroup_owner = dist_utils.xgroup_owner(p.xbins, p.zbins, self.world_size, self.device)
+                    self._xgroup_owner = dist_utils.xgroup_owner(p.xbins, p.zbins, self.world_size, self.device,
+                                                                 plan.group_points)
                     self._xgroup_owner_key = key
                 full = dist_utils.all_gather_select(mine, self._xgroup_owner)
             self.dE_dct = full[0].reshape(p.xbins, p.zbins)

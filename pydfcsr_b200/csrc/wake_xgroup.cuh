@@ -170,6 +170,34 @@ __device__ __noinline__ long long xg_move_window(int HT, int HZ, int Hhead, int 
     return ((long long)tw << 32) | (long long)(unsigned)zw;
 }
 
+// Same for lanes that carry several cells: [tlo, thi] x [zlo, zhi] per lane.
+template <bool kF32>
+__device__ __noinline__ long long xg_move_window_range(int HT, int HZ, int Hhead, int Hcap, bool ok, int tlo, int thi, int zlo,
+                                                       int zhi, const char* row0, const char* row1, double wy0, double yd,
+                                                       unsigned tile_s, unsigned slice_bytes) {
+    constexpr int VB = kF32 ? DFCSR_VOXEL_FLOATS * 4 : DFCSR_VOXEL_DOUBLES * 8;
+    const int lane = threadIdx.x & 31;
+    const int zmin = __reduce_min_sync(0xffffffffu, ok ? zlo : INT_MAX);
+    const int zmax = __reduce_max_sync(0xffffffffu, ok ? zhi : INT_MIN);
+    const int tmin = __reduce_min_sync(0xffffffffu, ok ? tlo : INT_MAX);
+    const int tmax = __reduce_max_sync(0xffffffffu, ok ? thi : INT_MIN);
+    if (tmin != tmax || zmax - zmin > kXWin - 2) return -1;
+    const int tw = tmin;
+    const int zw = max(0, min(zmin - ((kXWin - 2 - (zmax - zmin)) >> 1), HZ - kXWin));
+    const int ti = lane >> 4, zn = min(zw + (lane & (kXWin - 1)), HZ - 1);
+    int sl = Hhead + ((ti && tw != HT - 1) ? tw + 1 : tw);
+    sl -= (sl >= Hcap) ? Hcap : 0;
+    const size_t o = (size_t)((unsigned long long)(unsigned)sl * slice_bytes + (unsigned)zn * (unsigned)VB);
+    double y[5];
+    yblend_node<kF32>(row0 + o, row1 + o, wy0, yd, y);
+    __syncwarp();
+    sts128(tile_s + lane * 48, y[0], y[1]);
+    sts128(tile_s + lane * 48 + 16, y[2], y[3]);
+    sts64(tile_s + lane * 48 + 32, y[4]);
+    __syncwarp();
+    return ((long long)tw << 32) | (long long)(unsigned)zw;
+}
+
 // the two results of the group's points (CSR.py:588-589), x-major flattening of the mesh (CSR.py:382-389)
 __device__ __forceinline__ void xgroup_store(const MeshSrc& M, const dfcsr_wake_params& wp, const PeerOut& peers,
                                              double* out_dE, double* out_kick, int ix, int iz, bool lane_valid,
@@ -509,3 +537,348 @@ wake_xgroup_kernel(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupA
         atomicAdd(counters + 2, n_in);
     }
 }
+
+#ifdef DFCSR_DEV_VARIANTS
+// ---- MEASURED ALTERNATIVE, developer builds only: the same mapping with kP observation points per lane ----------------
+// Result on the bench launch (B200): 1.50 ms (128 threads x 3 CTAs) / 1.59 ms (192 x 2) / 1.95 ms (256 x 1) against 1.47 ms
+// for one point per lane at 16 warps per SM; bitwise the same grids.  Twice the instruction-level parallelism per warp at
+// three quarters of the warps buys nothing: the kernel is not waiting on its own dependent chains.
+// A group is 32 kP consecutive points of a mesh row; lane l carries points l, l + 32, ... of it.  The kP samples of a lane
+// at a step share the node record, x' n', 1 + x' kappa, the quadrature weight, the warp's window and all control flow; their
+// dependent fp64 chains are independent, so every warp offers the scheduler kP times the instruction-level parallelism (the
+// single-point kernel leaves the fp64 pipe 37 % idle waiting on dependent results).  Every point's own arithmetic and
+// summation order are exactly those of wake_xgroup_kernel: the two kernels give the same bits, and kP is a pure performance
+// choice of the plan.  Workspace per group: max_units x (64 kP) doubles.
+template <bool kF32, int kP, int kT, int kB>
+__global__ void __launch_bounds__(kT, kB)
+wake_xgroup_kernel_mp(HistDev H, LatDev L, dfcsr_wake_params wp, MeshSrc M, XGroupArgs A, double* __restrict__ out_dE,
+                      double* __restrict__ out_kick, unsigned long long* counters, const PeerOut peers) {
+    constexpr int VB = kF32 ? DFCSR_VOXEL_FLOATS * 4 : DFCSR_VOXEL_DOUBLES * 8;   // bytes per voxel
+    constexpr int GW = 32 * kP;                                                    // points per group
+    __shared__ XGroupShared sh;
+    extern __shared__ double2 xg_smem[];
+    double2* const node_tab2 = xg_smem + (kT / 32) * (2 * kXWin * 3);
+    double* const node_tab = reinterpret_cast<double*>(node_tab2);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int gl = (int)(blockIdx.x % (unsigned)A.ngroups);
+    const long long g = A.group_first + (long long)gl * A.group_stride;
+    const int ngx = (M.mx.n + GW - 1) / GW;
+    const int iz = (int)(g / ngx), gx = (int)(g - (long long)iz * ngx);
+    int ix[kP];
+    bool lane_valid[kP];
+#pragma unroll
+    for (int p = 0; p < kP; ++p) { ix[p] = gx * GW + p * 32 + lane; lane_valid[p] = ix[p] < M.mx.n; }
+    const int nz = wp.nz;
+    const int nzp = (nz + 31) & ~31;
+    unsigned tile_s = (unsigned)__cvta_generic_to_shared(reinterpret_cast<double*>(xg_smem) + warp * (2 * kXWin * 6));
+    asm volatile("mov.u32 %0, %0;" : "+r"(tile_s));
+
+    const double zz = axis_node(M.mz, iz);
+    const double shift = __dadd_rn(__dmul_rn(M.slope, zz), M.intercept);
+    if (threadIdx.x == 0) {
+        const double s = wp.t + zz;                       // CSR.py:412
+        const int ix_hi = min(gx * GW + GW - 1, M.mx.n - 1);
+        const double xa = __dadd_rn(axis_node(M.mx, gx * GW), shift), xb = __dadd_rn(axis_node(M.mx, ix_hi), shift);
+        sh.s = s;
+        sh.x_mid = 0.5 * (xa + xb);
+        sh.x_half = 0.5 * fabs(xb - xa);
+        int nreg;
+        build_regions(wp, H, s, sh.x_mid, sh.reg, nreg);
+        sh.nreg = nreg;
+        int base = 0;
+        for (int r = 0; r < nreg; ++r) {
+            sh.node_base[r] = base;
+            base += max(0, sh.reg[r].ihi - sh.reg[r].ilo + 1);
+        }
+        for (int r = nreg; r <= kMaxRegions; ++r) sh.node_base[r] = base;
+        for (int r = 0; r < kMaxRegions; ++r) { sh.jlo[r] = INT_MAX; sh.jhi[r] = -1; }
+        double v[6];
+        lattice_at(L, s, v);
+        sh.X0 = v[0]; sh.Y0 = v[1]; sh.nx = v[2]; sh.ny = v[3]; sh.tx = v[4]; sh.ty = v[5];
+        const int total = base, nun = (total + A.unit_nodes - 1) / A.unit_nodes;
+        sh.skip = (nun > 0 && *reinterpret_cast<volatile unsigned int*>(A.tickets + 2 * gl) >= (unsigned)nun) ? 1 : 0;
+    }
+    __syncthreads();
+    if (sh.skip) return;
+    const int nreg = sh.nreg;
+    fill_node_records_x(H, L, sh, wp.t, nz, nzp, node_tab, sh.jlo, sh.jhi);
+
+    const double Pt = wp.t;
+    double Pvx[kP], Pvy[kP], xnx[kP], xny[kP];
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+        const double x_obs = __dadd_rn(axis_node(M.mx, min(ix[p], M.mx.n - 1)), shift);
+        double f[5];
+        const double ut = (wp.t - H.min_t) * H.inv_dt, uy = (x_obs - H.min_x) * H.inv_dx;
+        const double uz = ((sh.s - wp.t) - H.min_z) * H.inv_dz;
+        const double vx = gather5<kF32>(H, ut, uy, uz, f) ? f[3] : 0.0;
+        Pvx[p] = add_rn(sh.tx, mul_rn(vx, sh.nx));            // vs*tau + vx*n with vs = 1
+        Pvy[p] = add_rn(sh.ty, mul_rn(vx, sh.ny));
+        xnx[p] = mul_rn(x_obs, sh.nx);
+        xny[p] = mul_rn(x_obs, sh.ny);
+    }
+    __syncthreads();
+
+    const char* const ring = reinterpret_cast<const char*>(H.ring);
+    const unsigned slice_bytes = (unsigned)H.slice_elems * (kF32 ? 4u : 8u);
+    const unsigned row_bytes = (unsigned)H.Z * (unsigned)VB;
+    const int total_nodes = sh.node_base[nreg];
+    const int U = A.unit_nodes;
+    const int nunits = (total_nodes + U - 1) / U;
+    double* const gpart = A.partials + (size_t)gl * A.max_units * (64 * kP);
+    unsigned long long n_in = 0;
+    const bool counting = counters != nullptr;
+    const int Zm1 = H.Z - 1, Tm1 = H.T - 1;
+    unsigned int* const q_next = A.tickets + 2 * gl;
+    unsigned int* const q_done = A.tickets + 2 * gl + 1;
+    if (nunits == 0) {
+        if (blockIdx.x < (unsigned)A.ngroups && warp == 0) {
+#pragma unroll
+            for (int p = 0; p < kP; ++p) xgroup_store(M, wp, peers, out_dE, out_kick, ix[p], iz, lane_valid[p], 0.0, 0.0);
+        }
+        return;
+    }
+    for (;;) {
+        unsigned int qi = 0;
+        if (lane == 0) qi = atomicAdd(q_next, 1u);
+        qi = __shfl_sync(0xffffffffu, qi, 0);
+        if (qi >= (unsigned)nunits) break;
+        const int u = nunits - 1 - (int)qi;
+        double acc_z[kP], acc_x[kP];
+#pragma unroll
+        for (int p = 0; p < kP; ++p) { acc_z[p] = 0.0; acc_x[p] = 0.0; }
+        const int n_end = min(total_nodes, (u + 1) * U);
+        for (int n = u * U; n < n_end; ++n) {
+            int r = 0;
+            while (r + 1 < nreg && n >= sh.node_base[r + 1]) ++r;
+            const int i = sh.reg[r].ilo + (n - sh.node_base[r]);
+            const Axis xa = sh.reg[r].xa;
+            const double xv = axis_node(xa, i);
+            const double uy = (xv - H.min_x) * H.inv_dx;
+            if (!cell_valid(uy, H.X)) continue;               // warp-uniform
+            int y0, y1;
+            double yd;
+            cell_split(uy, H.X, y0, y1, yd);
+            const double wy0 = 1.0 - yd;
+            const double x_prev = (i > 0) ? axis_node(xa, i - 1) : xv;
+            const double x_next = axis_node(xa, i + 1);
+            const double wx = 0.5 * ((x_next - xv) + (xv - x_prev));
+            const char* const row0 = ring + (size_t)((unsigned)y0 * (unsigned long long)row_bytes);
+            const char* const row1 = ring + (size_t)((unsigned)y1 * (unsigned long long)row_bytes);
+            const int j_lo = sh.jlo[r], j_hi = sh.jhi[r];
+            if (j_lo > j_hi) continue;
+            const double2* rec = node_tab2 + (size_t)(r * nzp + j_lo) * (kXRec / 2);
+            int tw = INT_MIN, zw = 0;
+            double kprev = 0.0, scale = 1.0, rscale = 1.0;
+            unsigned n_node = 0;
+
+            // geometry + cell coordinates of the kP samples at node record q (fast path of the fused sqrt, branch-free)
+            auto geometry = [&](const double2* q, double (&rx)[kP], double (&ry)[kP], double (&r2)[kP], double (&ir)[kP],
+                                double (&ut)[kP], double (&uz)[kP], bool (&fast)[kP]) {
+                const double2 r01 = q[0], r23 = q[1];
+                const double sp = q[3].y;
+                const double xnp = mul_rn(xv, r23.x), ynp = mul_rn(xv, r23.y);        // x' n'(s'): shared by the lane's points
+#pragma unroll
+                for (int p = 0; p < kP; ++p) {
+                    const double Cx = add_rn(r01.x, xnx[p]), Cy = add_rn(r01.y, xny[p]);
+                    rx[p] = sub_rn(Cx, xnp);
+                    ry[p] = sub_rn(Cy, ynp);
+                    r2[p] = add_rn(mul_rn(rx[p], rx[p]), mul_rn(ry[p], ry[p]));
+                    double rr;
+                    fast[p] = sqrt_pair_fast(r2[p], rr, ir[p]);
+                    const double t_ret = Pt - rr;
+                    ut[p] = (t_ret - H.min_t) * H.inv_dt;
+                    uz[p] = ((sp - t_ret) - H.min_z) * H.inv_dz;
+                }
+            };
+            auto fixup = [&](const double2* q, const bool (&fast)[kP], const double (&r2)[kP], double (&ir)[kP], double (&ut)[kP],
+                             double (&uz)[kP]) {
+#pragma unroll
+                for (int p = 0; p < kP; ++p) {
+                    if (!fast[p]) {                        // exceptional exponents (r = 0, inf, NaN): library path
+                        ir[p] = rsqrt(r2[p]);
+                        const double t_ret = Pt - __dsqrt_rn(r2[p]);
+                        ut[p] = (t_ret - H.min_t) * H.inv_dt;
+                        uz[p] = ((q[3].y - t_ret) - H.min_z) * H.inv_dz;
+                    }
+                }
+            };
+            auto gather = [&](const double (&ut)[kP], const double (&uz)[kP], const bool (&ok)[kP], double (&fld)[kP][5]) {
+                int t0[kP], z0[kP];
+                double td[kP], zd[kP];
+                bool inwin[kP];
+                bool need = false, any_ok = false;
+                int tlo = INT_MAX, thi = INT_MIN, zlo = INT_MAX, zhi = INT_MIN;
+#pragma unroll
+                for (int p = 0; p < kP; ++p) {
+                    t0[p] = ok[p] ? __double2int_rz(ut[p]) : tw;
+                    z0[p] = ok[p] ? __double2int_rz(uz[p]) : zw;
+                    td[p] = ut[p] - (double)t0[p];
+                    zd[p] = uz[p] - (double)z0[p];
+                    if (z0[p] == Zm1) { z0[p] = Zm1 - 1; zd[p] = 1.0; }
+                    inwin[p] = (t0[p] == tw) && ((unsigned)(z0[p] - zw) <= (unsigned)(kXWin - 2));
+                    need = need || (ok[p] && !inwin[p]);
+                }
+                if (__any_sync(0xffffffffu, need)) {
+#pragma unroll
+                    for (int p = 0; p < kP; ++p) {
+                        if (ok[p]) {
+                            any_ok = true;
+                            tlo = min(tlo, t0[p]); thi = max(thi, t0[p]); zlo = min(zlo, z0[p]); zhi = max(zhi, z0[p]);
+                        }
+                    }
+                    const long long moved = xg_move_window_range<kF32>(H.T, H.Z, H.head, H.cap, any_ok, tlo, thi, zlo, zhi, row0, row1,
+                                                                       wy0, yd, tile_s, slice_bytes);
+                    if (moved >= 0) {
+                        tw = (int)(moved >> 32);
+                        zw = (int)(moved & 0xffffffffll);
+#pragma unroll
+                        for (int p = 0; p < kP; ++p) inwin[p] = ok[p];
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < kP; ++p) {
+                    const double wt0 = 1.0 - td[p], wz0 = 1.0 - zd[p];
+                    const double w00 = wt0 * wz0, w01 = wt0 * zd[p], w10 = td[p] * wz0, w11 = td[p] * zd[p];
+                    double Y[4][5];
+                    if (inwin[p] || !ok[p]) {
+                        const unsigned a = tile_s + (inwin[p] ? (unsigned)(z0[p] - zw) * 48u : 0u);
+                        lds128(a, Y[0][0], Y[0][1]);           lds128(a + 16, Y[0][2], Y[0][3]);           lds64(a + 32, Y[0][4]);
+                        lds128(a + 48, Y[1][0], Y[1][1]);      lds128(a + 64, Y[1][2], Y[1][3]);           lds64(a + 80, Y[1][4]);
+                        lds128(a + 768, Y[2][0], Y[2][1]);     lds128(a + 784, Y[2][2], Y[2][3]);          lds64(a + 800, Y[2][4]);
+                        lds128(a + 816, Y[3][0], Y[3][1]);     lds128(a + 832, Y[3][2], Y[3][3]);          lds64(a + 848, Y[3][4]);
+                    } else {
+                        int s0 = H.head + t0[p];
+                        s0 -= (s0 >= H.cap) ? H.cap : 0;
+                        int s1 = s0 + 1;
+                        s1 = (s1 == H.cap) ? 0 : s1;
+                        s1 = (t0[p] == Tm1) ? s0 : s1;
+                        const unsigned zoff = (unsigned)z0[p] * (unsigned)VB;
+                        const size_t o0 = (size_t)((unsigned long long)(unsigned)s0 * slice_bytes + zoff);
+                        const size_t o1 = (size_t)((unsigned long long)(unsigned)s1 * slice_bytes + zoff);
+                        yblend_zrun<kF32>(row0 + o0, row1 + o0, wy0, yd, Y[0], Y[1]);
+                        yblend_zrun<kF32>(row0 + o1, row1 + o1, wy0, yd, Y[2], Y[3]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 5; ++q)
+                        fld[p][q] = fma(w11, Y[3][q], fma(w10, Y[2][q], fma(w01, Y[1][q], w00 * Y[0][q])));
+                }
+            };
+            auto algebra = [&](const double2* q, const double (&fld)[kP][5], const double (&rx)[kP], const double (&ry)[kP],
+                               const double (&ir)[kP], const bool (&ok)[kP]) {
+                const double2 r23 = q[1], r45 = q[2], r89 = q[4], rab = q[5];
+                const double nxp = r23.x, nyp = r23.y, txp = r45.x, typ = r45.y, ws = r89.x;
+                const double dnx = r89.y, dny = rab.x, q2 = rab.y;
+                const double w = ws * wx;
+                const double msq2 = mul_rn(-scale, q2);
+#pragma unroll
+                for (int p = 0; p < kP; ++p) {
+                    const double gz = div_by(fld[p][2], scale, rscale);
+                    const double rho = fld[p][0], rho_x = fld[p][1], vxr = fld[p][3], vxx = fld[p][4];
+                    const double vrx = add_rn(txp, mul_rn(vxr, nxp));
+                    const double vry = add_rn(typ, mul_rn(vxr, nyp));
+                    const double gxx = add_rn(mul_rn(rho_x, nxp), mul_rn(gz, txp));
+                    const double gyy = add_rn(mul_rn(rho_x, nyp), mul_rn(gz, typ));
+                    const double dot = add_rn(mul_rn(Pvx[p], vrx), mul_rn(Pvy[p], vry));
+                    const double ax = mul_rn(sub_rn(Pvx[p], mul_rn(dot, vrx)), gxx);
+                    const double ay = mul_rn(sub_rn(Pvy[p], mul_rn(dot, vry)), gyy);
+                    const double num1 = mul_rn(scale, add_rn(ax, ay));
+                    const double num2 = mul_rn(mul_rn(mul_rn(-scale, dot), rho), vxx);
+                    const double Iz = add_rn(mul_rn(num1, ir[p]), mul_rn(num2, ir[p]));
+                    const double q1 = add_rn(mul_rn(rx[p], dnx), mul_rn(ry[p], dny));
+                    const double drho = sub_rn(-add_rn(mul_rn(vrx, gxx), mul_rn(vry, gyy)), mul_rn(rho, vxx));
+                    const double sq1 = mul_rn(scale, q1);
+                    const double ir2 = mul_rn(ir[p], ir[p]);
+                    const double w1 = mul_rn(mul_rn(sq1, mul_rn(ir2, ir[p])), rho);
+                    const double w2 = mul_rn(mul_rn(sq1, ir2), drho);
+                    const double w3 = mul_rn(mul_rn(msq2, ir[p]), drho);
+                    const double Ix = add_rn(add_rn(w1, w2), w3);
+                    if (ok[p]) {
+                        acc_z[p] = fma(w, Iz, acc_z[p]);
+                        acc_x[p] = fma(w, Ix, acc_x[p]);
+                    }
+                }
+            };
+            auto new_scale = [&](double kappa) {
+                if (kappa != kprev) {
+                    kprev = kappa;
+                    scale = add_rn(1.0, mul_rn(xv, kappa));
+                    rscale = rcp_newton(scale);
+                }
+            };
+            auto in_grid = [&](const double (&ut)[kP], const double (&uz)[kP], bool live, bool (&ok)[kP]) {
+                bool any = false;
+#pragma unroll
+                for (int p = 0; p < kP; ++p) {
+                    ok[p] = live && lane_valid[p] && (ut[p] > -1.0) && (ut[p] < H.Td) && (uz[p] > -1.0) && (uz[p] < H.Zd);
+                    any = any || ok[p];
+                    if (counting) n_node += (unsigned)__popc(__ballot_sync(0xffffffffu, ok[p]));
+                }
+                return any;
+            };
+
+            double rx[kP], ry[kP], r2[kP], ir[kP], ut[kP], uz[kP], fld[kP][5];
+            bool fast[kP], ok[kP];
+            geometry(rec, rx, ry, r2, ir, ut, uz, fast);
+            fixup(rec, fast, r2, ir, ut, uz);
+            in_grid(ut, uz, true, ok);
+            new_scale(rec[3].x);
+            gather(ut, uz, ok, fld);
+            for (int j = j_lo; j <= j_hi; ++j, rec += kXRec / 2) {
+                double rxn[kP], ryn[kP], irn[kP];
+                geometry(rec + kXRec / 2, rxn, ryn, r2, irn, ut, uz, fast);        // node j + 1 (the table is padded by one record)
+                algebra(rec, fld, rx, ry, ir, ok);                                  // node j
+                fixup(rec + kXRec / 2, fast, r2, irn, ut, uz);
+                in_grid(ut, uz, j < j_hi, ok);
+                new_scale(rec[kXRec / 2 + 3].x);
+                gather(ut, uz, ok, fld);
+#pragma unroll
+                for (int p = 0; p < kP; ++p) { rx[p] = rxn[p]; ry[p] = ryn[p]; ir[p] = irn[p]; }
+            }
+            n_in += n_node;
+        }
+        double* const row = gpart + (size_t)u * (64 * kP);
+#pragma unroll
+        for (int p = 0; p < kP; ++p) {
+            __stcg(row + p * 64 + lane, acc_z[p]);
+            __stcg(row + p * 64 + 32 + lane, acc_x[p]);
+        }
+        __threadfence();
+        __syncwarp();
+        unsigned int done = 0;
+        if (lane == 0) done = atomicAdd(q_done, 1u);
+        done = __shfl_sync(0xffffffffu, done, 0);
+        if (done == (unsigned)nunits - 1u) {
+            __threadfence();
+#pragma unroll 1
+            for (int p = 0; p < kP; ++p) {
+                double z = 0.0, xk = 0.0;
+                int v = 0;
+                const double* base = gpart + p * 64 + lane;
+                for (; v + 4 <= nunits; v += 4) {
+                    const double* q = base + (size_t)v * (64 * kP);
+                    const double a0 = __ldcg(q), a1 = __ldcg(q + 64 * kP), a2 = __ldcg(q + 128 * kP), a3 = __ldcg(q + 192 * kP);
+                    const double b0 = __ldcg(q + 32), b1 = __ldcg(q + 64 * kP + 32), b2 = __ldcg(q + 128 * kP + 32), b3 = __ldcg(q + 192 * kP + 32);
+                    z += a0; z += a1; z += a2; z += a3;
+                    xk += b0; xk += b1; xk += b2; xk += b3;
+                }
+                for (; v < nunits; ++v) {
+                    z += __ldcg(base + (size_t)v * (64 * kP));
+                    xk += __ldcg(base + (size_t)v * (64 * kP) + 32);
+                }
+                xgroup_store(M, wp, peers, out_dE, out_kick, gx * GW + p * 32 + lane, iz, gx * GW + p * 32 + lane < M.mx.n, z, xk);
+            }
+            if (lane == 0 && counters) {
+                unsigned long long full = 0;
+                for (int r = 0; r < nreg; ++r) full += (unsigned long long)sh.reg[r].xa.n * (unsigned long long)nz;
+                atomicAdd(counters + 1, full * (unsigned long long)min(GW, M.mx.n - gx * GW));
+            }
+        }
+    }
+    if (counters && lane == 0 && n_in) {
+        atomicAdd(counters + 0, n_in);
+        atomicAdd(counters + 2, n_in);
+    }
+}
+#endif  // DFCSR_DEV_VARIANTS

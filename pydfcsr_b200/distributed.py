@@ -53,12 +53,13 @@ def all_gather_blocks(send: torch.Tensor, count, n: int) -> torch.Tensor:
     return torch.cat([recv[p, :, :count[p]] for p in range(world)], dim=1)
 
 
-def xgroup_owner(nx: int, nz: int, world: int, device) -> torch.Tensor:
-    """Rank that computes mesh point (ix, iz) when x-groups are dealt out round-robin (group = iz * ceil(nx/32) + ix // 32,
-    flat index = ix * nz + iz as in get_CSR_mesh, CSR.py:382-389)."""
+def xgroup_owner(nx: int, nz: int, world: int, device, group_points: int = 32) -> torch.Tensor:
+    """Rank that computes mesh point (ix, iz) when x-groups are dealt out round-robin (group = iz * ceil(nx/gw) + ix // gw
+    with gw = dfcsr_xgroup_plan.group_points, flat index = ix * nz + iz as in get_CSR_mesh, CSR.py:382-389)."""
+    gw = int(group_points)
     ix = torch.arange(nx, device=device).unsqueeze(1)
     iz = torch.arange(nz, device=device).unsqueeze(0)
-    return ((iz * ((nx + 31) // 32) + ix // 32) % world).reshape(-1)
+    return ((iz * ((nx + gw - 1) // gw) + ix // gw) % world).reshape(-1)
 
 
 def all_gather_select(mine: torch.Tensor, owner: torch.Tensor) -> torch.Tensor:

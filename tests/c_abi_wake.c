@@ -87,7 +87,7 @@ int main(void) {
     CHECK(dfcsr_wake_grid(&h, &lt, &wp, m_x, m_z, 0.0, 0.0, 0, N, d_a, d_a + N, d_cnt, NULL));
     dfcsr_xgroup_plan plan;
     CHECK(dfcsr_wake_xgroup_plan(&h, &wp, m_x, m_z, &plan));
-    if (plan.n_groups != 2 * MZ) { fprintf(stderr, "plan: %lld groups\n", (long long)plan.n_groups); return 1; }
+    if (plan.n_groups != 2 * MZ || plan.group_points != 32) { fprintf(stderr, "plan: %lld groups\n", (long long)plan.n_groups); return 1; }
     void* d_ws; const int64_t ws_bytes = plan.n_groups * plan.workspace_bytes_per_group;
     CU(cudaMalloc(&d_ws, (size_t)ws_bytes));
     CHECK(dfcsr_wake_grid_xgroups(&h, &lt, &wp, m_x, m_z, 0.0, 0.0, 0, plan.n_groups, 1, d_b, d_b + N, NULL, 0, d_ws, ws_bytes, NULL, NULL));

@@ -118,11 +118,11 @@ for n in (7, 10, 4096):
     assert np.array_equal(got, full), (rank, n)
 # x-groups dealt out round-robin (group = iz * ceil(nx/32) + ix // 32, rank = group % world): every rank fills its own
 # points of a full grid; the exchange copies every point from its owner (-0.0 stays -0.0, NaN placeholders never leak)
-for nx, nz in ((32, 5), (48, 7), (70, 3)):
+for nx, nz, gw in ((32, 5, 32), (48, 7, 64), (70, 3, 32), (128, 3, 64)):
     n = nx * nz
-    owner = D.xgroup_owner(nx, nz, world, torch.device("cpu"))
+    owner = D.xgroup_owner(nx, nz, world, torch.device("cpu"), gw)
     ix, iz = np.divmod(np.arange(n), nz)
-    assert np.array_equal(owner.numpy(), (iz * ((nx + 31) // 32) + ix // 32) % world)
+    assert np.array_equal(owner.numpy(), (iz * ((nx + gw - 1) // gw) + ix // gw) % world)
     full = -np.arange(2 * n, dtype=np.float64).reshape(2, n)          # element 0 is -0.0
     mine = torch.full((2, n), float("nan"), dtype=torch.float64)
     sel = (owner == rank)

@@ -38,18 +38,19 @@ def _mesh(sc, xbins, zbins):
     return xm, zm, Axis.make(xr[0], xr[-1], xbins), Axis.make(zr[0], zr[-1], zbins), float(s["slope"][0]), float(s["slope"][1])
 
 
-@pytest.mark.parametrize("tilt,xbins,zbins,nx,nz", [(0.0, 32, 5, 40, 40), (0.5, 48, 3, 50, 33), (-0.7, 70, 2, 24, 64)])
-def test_xgroup_matches_oracle_and_point_kernel(dev, tilt, xbins, zbins, nx, nz):
-    """Full and partial groups (48 = 32 + 16 lanes, 70 = 32 + 32 + 6), straight and tilted bunches below the chirp-band
-    switch, ragged integration meshes: oracle parity on every mesh point, agreement with the point kernel far below the
-    gate, sample accounting identical to the point kernel's."""
+@pytest.mark.parametrize("tilt,xbins,zbins,nx,nz,gw", [(0.0, 32, 5, 40, 40, 32), (0.5, 48, 3, 50, 33, 32),
+                                                          (-0.7, 70, 2, 24, 64, 32), (0.0, 128, 2, 40, 40, 32)])
+def test_xgroup_matches_oracle_and_point_kernel(dev, tilt, xbins, zbins, nx, nz, gw):
+    """Full and partial groups (48 = 32 + 16 lanes, 70 = 32 + 32 + 6, 128 = 4 x 32), straight and tilted bunches below the
+    chirp-band switch, ragged integration meshes: oracle parity on every mesh point, agreement with the point kernel far
+    below the gate, sample accounting identical to the point kernel's."""
     import torch
     from pydfcsr_b200 import ops
     sc = scenario.chicane_entry(tilt=tilt)
     hist, dlat, wp, osc = _problem(sc, dev, nx, nz)
     xm, zm, xa, za, slope, icpt = _mesh(sc, xbins, zbins)
     plan = ops.wake_xgroup_plan(hist, wp, xa, za)
-    assert plan.n_groups == zbins * ((xbins + 31) // 32) and plan.unit_nodes >= 1
+    assert plan.group_points == gw and plan.n_groups == zbins * ((xbins + gw - 1) // gw) and plan.unit_nodes >= 1
     cnt = torch.zeros(3, dtype=torch.int64, device=dev)
     de, kick = ops.wake_grid_xgroups(hist, dlat, wp, xa, za, slope, icpt, plan=plan, counters=cnt)
     cnt_p = torch.zeros(3, dtype=torch.int64, device=dev)
@@ -64,21 +65,23 @@ def test_xgroup_matches_oracle_and_point_kernel(dev, tilt, xbins, zbins, nx, nz)
     assert torch.equal(de, de2) and torch.equal(kick, kick2)
 
 
-def test_xgroup_result_is_independent_of_the_split(dev):
+@pytest.mark.parametrize("xbins,zbins,gw", [(70, 5, 32), (112, 5, 32)])
+def test_xgroup_result_is_independent_of_the_split(dev, xbins, zbins, gw):
     """Groups dealt out round-robin to 3 'ranks', in two contiguous blocks, one by one, and written through 'peer'
-    grids (three grids of this GPU): always the bits of the single launch."""
+    grids (three grids of this GPU): always the bits of the single launch.  70 = 32 + 32 + 6 points per row, 112 = 3 x 32 + 16."""
     import torch
     from pydfcsr_b200 import ops
     sc = scenario.chicane_entry(tilt=0.0)
     hist, dlat, wp, _ = _problem(sc, dev, 40, 40)
-    xm, zm, xa, za, slope, icpt = _mesh(sc, 48, 7)            # 7 rows x (32 + 16 lanes) = 14 groups
+    xm, zm, xa, za, slope, icpt = _mesh(sc, xbins, zbins)
     plan = ops.wake_xgroup_plan(hist, wp, xa, za)
-    assert plan.n_groups == 14
-    n = 48 * 7
+    ng = zbins * ((xbins + gw - 1) // gw)
+    assert plan.n_groups == ng and plan.group_points == gw
+    n = xbins * zbins
     de, kick = ops.wake_grid_xgroups(hist, dlat, wp, xa, za, slope, icpt, plan=plan)
     splits = {"stride 3": [(r, None, 3) for r in range(3)],
-              "two blocks": [(0, 5, 1), (5, 9, 1)],
-              "one by one": [(g, 1, 1) for g in range(14)]}
+              "two blocks": [(0, 5, 1), (5, ng - 5, 1)],
+              "one by one": [(g, 1, 1) for g in range(ng)]}
     for label, parts in splits.items():
         out = torch.full((2, n), float("nan"), dtype=torch.float64, device=dev)
         for first, count, stride in parts:
@@ -115,7 +118,7 @@ def test_xgroup_plan_rules(dev):
     _, _, xa_big, za_big, _, _ = _mesh(sc, 64, 512)
     wp_big = ops.wake_params(nx=200, nz=200, skip="off", **sc["wake_scalars"])
     big = ops.wake_xgroup_plan(hist, wp_big, xa_big, za_big)
-    assert big.n_groups == 1024 and 1 < big.unit_nodes <= 8 and big.max_units * big.unit_nodes >= 800
+    assert big.group_points == 32 and big.n_groups == 1024 and 1 < big.unit_nodes <= 8 and big.max_units * big.unit_nodes >= 800
 
 
 def test_xgroup_empty_quadrature_and_fp32(dev):
