@@ -16,6 +16,8 @@ from __future__ import annotations
 from collections import deque
 from dataclasses import dataclass
 
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -95,6 +97,8 @@ class DF_tracker:
     # ------------------------------------------------------------------------------- get_DF
     def _as_device(self, a):
         if isinstance(a, torch.Tensor):
+            if a.is_cuda and a.dtype == torch.float64 and a.is_contiguous() and a.device == self.device:
+                return a                      # the usual case (Beam's coordinate arrays): nothing to do, nothing to call
             return a.to(self.device, torch.float64).contiguous()
         return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device, non_blocking=True)
 
@@ -135,9 +139,9 @@ class DF_tracker:
             # same two stages on one GPU (max|px| came with the statistics: no separate reduction pass over px)
             if self._q_scratch is None or self._q_scratch.numel() < 2 * xb * zb:
                 self._q_scratch = torch.empty(2 * xb * zb, dtype=torch.int64, device=self.device)
-            import ctypes as C
+                self._q_ptrs = (C.c_uint64 * 1)(self._q_scratch.data_ptr())
             ops.deposit_cic_q(x, z, px, x.numel(), xb, x_lo, x_hi, zb, z_lo, z_hi, absmax, self._q_scratch)
-            count, vxsum = ops.deposit_cic_finish((C.c_uint64 * 1)(self._q_scratch.data_ptr()), x.numel(), xb, zb, absmax,
+            count, vxsum = ops.deposit_cic_finish(self._q_ptrs, x.numel(), xb, zb, absmax,
                                                   out=self._deposit_scratch, count_max=self._count_max)
             cmax = self._count_max
         else:

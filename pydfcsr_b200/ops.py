@@ -18,14 +18,16 @@ from ._lib import Axis, check, lib
 F64 = torch.float64
 
 
-def _ptr(t: torch.Tensor | None) -> C.c_void_p:
+def _ptr(t: torch.Tensor | None):
+    """Device address of a contiguous CUDA tensor as a plain int (ctypes converts ints and None for `c_void_p` parameters
+    itself: no wrapper object per argument -- a lattice step passes ~50 pointers on the host's critical path)."""
     if t is None:
-        return C.c_void_p(0)
+        return None
+    if t.is_cuda and t.is_contiguous():
+        return t.data_ptr()
     if not t.is_cuda:
         raise _lib.DfcsrError("pydfcsr_b200 kernels need CUDA tensors (there is no CPU fallback)")
-    if not t.is_contiguous():
-        raise _lib.DfcsrError("tensor must be contiguous")
-    return C.c_void_p(t.data_ptr())
+    raise _lib.DfcsrError("tensor must be contiguous")
 
 
 def _f64(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -35,15 +37,17 @@ def _f64(t: torch.Tensor, name: str) -> torch.Tensor:
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
 
 
-def _stream() -> C.c_void_p:
+def _stream():
     """The current torch stream of the current device as a raw cudaStream_t (every kernel of the library is enqueued on
-    it).  torch.cuda.current_stream() costs ~10 us of Python per call -- a dozen calls per lattice step sit on the
-    host's critical path between the statistics and the wake launch -- so the raw C accessor is used when torch has it."""
+    it).  torch.cuda.current_stream() costs ~10 us of Python per call and torch.cuda.current_device() ~2 us -- a dozen calls
+    per lattice step sit on the host's critical path between the statistics and the wake launch -- so the raw C accessors
+    are used when torch has them."""
     if _raw_stream is not None:
-        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return _raw_stream(_raw_device() if _raw_device is not None else torch.cuda.current_device())
+    return torch.cuda.current_stream().cuda_stream
 
 
 # ---------------------------------------------------------------------------------------------
@@ -269,6 +273,7 @@ def savgol_operators(window: int, order: int):
 
 
 _df_ws: dict = {}
+_df_need: dict = {}
 _sg_dev: dict = {}
 
 
@@ -278,7 +283,9 @@ def make_df(count, vxsum, x_axis: Axis, z_axis: Axis, window: int, order: int, v
     tensor filled by deposit_cic_finish (saves the reduction launch)."""
     nx, nz = x_axis.n, z_axis.n
     dev = count.device
-    need = lib.dfcsr_make_df_workspace(nx, nz)
+    need = _df_need.get((nx, nz))
+    if need is None:
+        need = _df_need[(nx, nz)] = lib.dfcsr_make_df_workspace(nx, nz)
     ws = _df_ws.get(dev)
     if ws is None or ws.numel() < need:
         ws = _df_ws[dev] = torch.empty(need, dtype=torch.uint8, device=dev)
@@ -436,8 +443,11 @@ class DeviceLattice:
                    float(min_s), float(delta_s))
 
     def view(self) -> _lib.Lattice:
-        return _lib.Lattice(self.table.data_ptr(), self.table.shape[0], self.rho.numel(), self.min_s, self.delta_s,
-                            self.rho.data_ptr(), self.distance.data_ptr())
+        v = self.__dict__.get("_view")            # the tables never change after upload: build the struct once
+        if v is None:
+            v = self.__dict__["_view"] = _lib.Lattice(self.table.data_ptr(), self.table.shape[0], self.rho.numel(),
+                                                      self.min_s, self.delta_s, self.rho.data_ptr(), self.distance.data_ptr())
+        return v
 
 
 @dataclass
@@ -554,7 +564,9 @@ def wake_grid_xgroups(hist: DeviceHistory, lat: DeviceLattice, wp: _lib.WakePara
         group_count = (plan.n_groups - group_first + group_stride - 1) // group_stride
     dev = hist.ring.device
     if out is None and peer_ptrs is None:
-        out = torch.zeros((2, n), dtype=F64, device=dev)
+        # a launch over all groups writes every mesh point: no fill needed
+        whole = group_first == 0 and group_stride == 1 and group_count == plan.n_groups
+        out = (torch.empty if whole else torch.zeros)((2, n), dtype=F64, device=dev)
     ws = xgroup_workspace(dev, group_count * plan.workspace_bytes_per_group)
     hv, lv = hist.view(), lat.view()
     check(lib.dfcsr_wake_grid_xgroups(C.byref(hv), C.byref(lv), C.byref(wp), x_axis, z_axis, float(slope), float(intercept),
