@@ -232,6 +232,16 @@ int dfcsr_make_df(const double* d_count, const double* d_vxsum, dfcsr_axis x_axi
                   double velocity_threshold, const uint64_t* d_count_max, double* d_fields, double* d_scalars,
                   void* d_workspace, void* stream);
 
+/* DF_tracker.get_DF (deposit.py:145-245) on one GPU in ONE call: dfcsr_deposit_cic_q + dfcsr_deposit_cic_finish +
+ * dfcsr_make_df back to back on `stream` with the same arguments and the same results (the five kernels are the
+ * same; only the host round trips between them are gone: three binding calls cost ~100 us of host time per lattice
+ * step, more than the kernels take).  d_q: (2, nx*nz) int64 scratch; d_count / d_vxsum: the deposit grids (outputs,
+ * kept for the caller); d_count_max: one uint64 of scratch. */
+int dfcsr_get_df(const double* d_x, const double* d_z, const double* d_px, int64_t n, dfcsr_axis x_axis, dfcsr_axis z_axis,
+                 double absmax_px, int64_t* d_q, double* d_count, double* d_vxsum, uint64_t* d_count_max,
+                 int32_t window, const double* d_taps, const double* d_edge_lo, const double* d_edge_hi,
+                 double velocity_threshold, double* d_fields, double* d_scalars, void* d_workspace, void* stream);
+
 /* ---- A7 / K3 bilinear re-gridding into a history slot (deposit.py:296-309,328-332,379-390) -----
  * Samples the five fields of one raw density-function record (field stack on src axes) on the
  * history grid and writes one voxel slice.  Out-of-source points get 0, or the fill value for vx_x

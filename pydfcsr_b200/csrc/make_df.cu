@@ -518,3 +518,20 @@ extern "C" int dfcsr_make_df(const double* d_count, const double* d_vxsum, dfcsr
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;
 }
+
+// DF_tracker.get_DF on one GPU in one call (include/dfcsr_b200.h): the three stages back to back on one stream
+extern "C" int dfcsr_get_df(const double* d_x, const double* d_z, const double* d_px, int64_t n, dfcsr_axis x_axis,
+                            dfcsr_axis z_axis, double absmax_px, int64_t* d_q, double* d_count, double* d_vxsum,
+                            uint64_t* d_count_max, int32_t window, const double* d_taps, const double* d_edge_lo,
+                            const double* d_edge_hi, double velocity_threshold, double* d_fields, double* d_scalars,
+                            void* d_workspace, void* stream) {
+    DFCSR_REQUIRE(d_q && d_count && d_vxsum && d_count_max, "null scratch / output pointer");
+    int rc = dfcsr_deposit_cic_q(d_x, d_z, d_px, n, n, x_axis.n, x_axis.start, x_axis.stop, z_axis.n, z_axis.start, z_axis.stop,
+                                 absmax_px, d_q, stream);
+    if (rc) return rc;
+    const uint64_t self = static_cast<uint64_t>(reinterpret_cast<uintptr_t>(d_q));
+    rc = dfcsr_deposit_cic_finish(&self, 1, x_axis.n, z_axis.n, n, absmax_px, d_count, d_vxsum, d_count_max, stream);
+    if (rc) return rc;
+    return dfcsr_make_df(d_count, d_vxsum, x_axis, z_axis, window, d_taps, d_edge_lo, d_edge_hi, velocity_threshold,
+                         d_count_max, d_fields, d_scalars, d_workspace, stream);
+}

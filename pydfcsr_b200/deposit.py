@@ -136,14 +136,16 @@ class DF_tracker:
                                                   count_max=self._count_max)
             cmax = self._count_max
         elif self.deposit_mode == 0 and absmax >= 0.0:
-            # same two stages on one GPU (max|px| came with the statistics: no separate reduction pass over px)
+            # the same two deposit stages and the density functions on one GPU, in ONE binding call (max|px| came with
+            # the statistics: no separate reduction pass over px)
             if self._q_scratch is None or self._q_scratch.numel() < 2 * xb * zb:
                 self._q_scratch = torch.empty(2 * xb * zb, dtype=torch.int64, device=self.device)
-                self._q_ptrs = (C.c_uint64 * 1)(self._q_scratch.data_ptr())
-            ops.deposit_cic_q(x, z, px, x.numel(), xb, x_lo, x_hi, zb, z_lo, z_hi, absmax, self._q_scratch)
-            count, vxsum = ops.deposit_cic_finish(self._q_ptrs, x.numel(), xb, zb, absmax,
-                                                  out=self._deposit_scratch, count_max=self._count_max)
-            cmax = self._count_max
+            x_axis, z_axis = Axis.make(x_lo, x_hi, xb), Axis.make(z_lo, z_hi, zb)
+            fields, scalars = ops.get_df(x, z, px, x_axis, z_axis, absmax, window, self.filter_order, self.velocity_threhold,
+                                         self._q_scratch, self._deposit_scratch, self._count_max)
+            self._current = _Record(fields, scalars, x_axis, z_axis, t, sigma_x, sigma_z, xmean, zmean)
+            self.t = t
+            return
         else:
             count, vxsum = ops.deposit_cic(x, z, px, xb, x_lo, x_hi, zb, z_lo, z_hi, mode=self.deposit_mode,
                                            out=self._deposit_scratch)

@@ -627,3 +627,31 @@ def test_track_element_kernel_reproduces_bmadx_known_answers(dev):
             scale = max(np.max(np.abs(want[k])), 1e-300)
             # FMA contraction on the device; z of a bend is a difference of O(L) path lengths (measured 1.4e-13)
             assert np.max(np.abs(got[k].cpu().numpy() - want[k])) <= 1e-12 * scale, (el, k)
+
+
+def test_get_df_composite_is_bitwise_the_three_calls(dev):
+    """dfcsr_get_df (one binding call) = dfcsr_deposit_cic_q + dfcsr_deposit_cic_finish + dfcsr_make_df: the same five
+    kernels with the same arguments, so fields, scalars and deposit grids must be the same bits (deposit.py:145-245)."""
+    import ctypes as C
+    import torch
+    from pydfcsr_b200 import ops
+    from pydfcsr_b200._lib import Axis
+    rng = np.random.default_rng(5)
+    n = 200_000
+    x, z, px = (_up(rng.normal(0, s, n), dev) for s in (1e-4, 2e-4, 1e-5))
+    for (nx, nz, window, order) in ((100, 100, 5, 1), (64, 96, 9, 1), (300, 300, 9, 2)):
+        xa, za = Axis.make(-5e-4, 5e-4, nx), Axis.make(-1e-3, 1e-3, nz)
+        absmax = float(px.abs().max())
+        q = torch.empty(2 * nx * nz, dtype=torch.int64, device=dev)
+        cmax = torch.zeros(1, dtype=torch.int64, device=dev)
+        dep = torch.empty((2, nx, nz), dtype=torch.float64, device=dev)
+        ops.deposit_cic_q(x, z, px, n, nx, xa.start, xa.stop, nz, za.start, za.stop, absmax, q)
+        c, v = ops.deposit_cic_finish((C.c_uint64 * 1)(q.data_ptr()), n, nx, nz, absmax, out=dep, count_max=cmax)
+        f0, s0 = ops.make_df(c, v, xa, za, window, order, 1000.0, count_max=cmax)
+        dep0 = dep.clone()
+        q2 = torch.empty_like(q)
+        cmax2 = torch.zeros_like(cmax)
+        dep2 = torch.empty_like(dep)
+        f1, s1 = ops.get_df(x, z, px, xa, za, absmax, window, order, 1000.0, q2, dep2, cmax2)
+        assert torch.equal(dep2, dep0) and torch.equal(f1, f0) and torch.equal(s1, s0) and torch.equal(cmax2, cmax)
+        assert float(f1[0].abs().max()) > 0
