@@ -12,11 +12,16 @@
 // and the L1 -> register path (320 B per lane-sample) is its binding unit (profiles/k4_r2_bench.txt).
 //
 // Mapping here: a GROUP = up to 32 mesh points with the same z index and consecutive x indices; lane = point.  A warp
-// walks one x' node through the s' nodes IN SEQUENCE.  Per step all lanes share the node record (one broadcast read),
-// the history rows and the transverse fraction; each lane keeps the four transverse-blended (t', z) corners of its
-// current cell in registers (20 doubles) and reloads them only when ITS cell changes: in the middle rectangle that is
-// about once per x' node, in the far rectangle every ~11 nodes; ahead of the observer (z_ret moves 2-7 cells per node)
-// every step, which costs what the direct gather costs.  A hit needs no history load at all and a 4-corner blend.
+// walks one x' node through the s' nodes IN SEQUENCE.  Per step all lanes share the node record (broadcast reads), the two
+// history rows and the transverse fraction, and they look at nearly the same place of the (t', z) plane: the warp keeps
+// the transverse-blended history nodes of a 2 x 16 window around that place in shared memory (one node per lane when the
+// window is refilled) and a sample reads its four corners from there -- 12 shared-memory loads and a 4-corner blend
+// instead of 24 global loads and an 8-corner blend.  The window follows the sweep (a refill every ~25-80 steps); a lane
+// that is outside it (near the observer r depends strongly on x: 6 % of the warp-steps on the bench workload) blends its
+// corners from global memory with the same operations, so the bits do not depend on the path.  The sweep is software-
+// pipelined: the dependent geometry chain of node j + 1 is issued next to the independent integrand algebra of node j.
+// (First version: four corners per lane cached in registers, reloaded when the lane changed cell -- that divergent path
+// ran in 53 % of the steps with 7 of 32 lanes active; profiles/k4_r2_xgroup_variants.txt has all the steps.)
 //
 // Work split and summation order (bitwise independent of the launch geometry and of the rank split):
 //   * the pruned x' nodes of all rectangles form one list; UNIT u = nodes [u U, (u+1) U) of it; a warp accumulates a
