@@ -181,3 +181,35 @@ def test_parameter_blocks_mirror_reference_defaults():
     assert cp.write_wakes is True and cp.write_beam == [16, 17] and os.path.isabs(cp.workdir) and cp.write_name == ""
     with pytest.raises(TypeError):
         CSR_params({"not_a_key": 1})
+
+
+def test_xgroup_plan_is_host_arithmetic():
+    """dfcsr_wake_xgroup_plan touches no device memory: it can be pinned on the CPU.  The plan (which K4 mapping runs, unit
+    size, scratch per group) must be a function of the history geometry, the beam scalars and the WHOLE mesh -- the rule
+    every rank of a parallel run relies on to take the same decision (CSR.py:420-451 splits the mesh, not the physics)."""
+    import ctypes as C
+    from pydfcsr_b200 import _lib
+    from pydfcsr_b200._lib import Axis
+
+    def plan(xbins=64, zbins=64, slope0=-0.4, sigma_z=2.0e-4, skip="off", support=1, nx=200, nz=200, X=500, Z=500):
+        sx = 1.0e-4
+        hist = _lib.History(0x1000, X * Z * 6, 16, 0, 7, X, Z, 0, 0.0, -5 * sx, -5 * sigma_z, 0.1, 10 * sx / (X - 1),
+                            10 * sigma_z / (Z - 1), 0x2000 if support else None)
+        wp = _lib.WakeParams(0.6, sx, sigma_z, slope0, 0.0, 0.5, 1e-5, nx, nz, _lib.SKIP_MODES[skip], 0)
+        out = _lib.XGroupPlan()
+        xa, za = Axis.make(-3 * sx, 3 * sx, xbins), Axis.make(-3 * sigma_z, 3 * sigma_z, zbins)
+        assert _lib.lib.dfcsr_wake_xgroup_plan(C.byref(hist), C.byref(wp), xa, za, C.byref(out)) == 0
+        return out
+
+    p = plan()
+    assert (p.n_groups, p.group_points, p.unit_nodes, p.max_units) == (128, 32, 1, 800)
+    assert p.workspace_bytes_per_group == 800 * 64 * 8 + 256
+    assert plan(xbins=64, zbins=512).n_groups == 1024 and plan(xbins=64, zbins=512).unit_nodes == 2      # larger units on larger meshes
+    assert plan(xbins=10, zbins=30).n_groups == 0                 # 10 of 32 lanes would carry a point
+    assert plan(xbins=23).n_groups == 64 and plan(xbins=22).n_groups == 0
+    assert plan(slope0=1.5).n_groups == 0 and plan(slope0=-1.0).n_groups == 128      # chirp band (CSR.py:480)
+    assert plan(skip="on").n_groups == 0 and plan(skip="on", support=0).n_groups == 128   # skipping needs the row-support table
+    assert plan(skip="auto").n_groups == 128                      # a bunch that fills its grid: AUTO does not skip
+    assert plan(skip="auto", X=2000).n_groups == 128 and plan(skip="auto", sigma_z=2.0e-4, Z=500, X=500).n_groups == 128
+    assert plan(sigma_z=2.0e-5).n_groups == 0                     # compressed bunch: a group spreads over ~80 history cells
+    assert plan(nz=400).n_groups == 0                             # node table would not leave room for two CTAs per SM
