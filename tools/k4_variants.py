@@ -2,8 +2,12 @@
 tools/build_dev.py) on the bench workload in ONE process and compare each variant's wake grids with the first one.
 
     python tools/build_dev.py && DFCSR_LIB=pydfcsr_b200/libdfcsr_b200_dev.so python tools/k4_variants.py [reps] [cfg ...]
-    DFCSR_TILT=2.5 adds an x-z tilt (chirp-band quadrature); cfg 0 = shipped kernel, 20 / 40 = without bracket and queue interleave,
-    30 = register cache, 25 = two x' nodes per lane, 70 = patch kernel (71.. = patch of 0, 8, 16, ... nodes per warp), 80 = lean node records
+    DFCSR_TILT=2.5 adds an x-z tilt (chirp-band quadrature); cfg 0 = shipped kernels.
+    Point mapping (DFCSR_WAKE_MAPPING=point or a chirp-band / sparse step): 20 / 40 = without bracket and queue interleave, 30 = register
+    cache, 25 = two x' nodes per lane, 70 = patch kernel (71.. = patch of 0, 8, 16, ... nodes per warp), 80 = lean node records, 90 = prefetch.
+    x-group mapping (the bench workload's default): 1 = unpipelined sweep, 2 = 192 x 3 CTAs, 3 / 4 = two steps per iteration, 5 = 320 x 2,
+    6 = 384 x 2, 7 / 8 / 10 = two observation points per lane (256 x 1, 128 x 3, 192 x 2), 9 = plan without the spread criterion,
+    11..19 = 1, 2, 3, 4, 7, 10, 13, 16, 19 CTAs per group
 """
 import os
 import sys
