@@ -280,6 +280,7 @@ def gpu_arm(args):
     def hot_path(timed_k4, sink=None):
         beam.update_status()
         b = beam
+        trk.prefetch_DF(b)            # as CSR2D.run does: deposit + density functions enqueued behind the statistics pass
         trk.get_DF(x=b.x, z=b.z, px=b.px, t=b.position, stats=b.stats)
         trk.append_DF()
         trk.append_interpolant(formation_length=csr.formation_length,
@@ -555,6 +556,7 @@ def _one_step(csr, events=None):
     import torch
     b, trk = csr.beam, csr.DF_tracker
     b.update_status()
+    trk.prefetch_DF(b)
     trk.get_DF(x=b.x, z=b.z, px=b.px, t=b.position, stats=b.stats)
     trk.append_DF()
     trk.append_interpolant(formation_length=csr.formation_length, n_formation_length=csr.integration_params.n_formation_length)

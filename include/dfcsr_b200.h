@@ -242,6 +242,19 @@ int dfcsr_get_df(const double* d_x, const double* d_z, const double* d_px, int64
                  int32_t window, const double* d_taps, const double* d_edge_lo, const double* d_edge_hi,
                  double velocity_threshold, double* d_fields, double* d_scalars, void* d_workspace, void* stream);
 
+/* The same, enqueued BEFORE the host has read the statistics: the grid limits mean -+ lim * sigma (deposit.py:160-171)
+ * and max|px| are taken from d_stats, the DEVICE vector dfcsr_beam_stats is writing on the same stream, by a one-thread
+ * kernel that evaluates the Python expression with its roundings; d_limits (4 doubles, caller-owned) receives
+ * {x_lo, x_hi, z_lo, z_hi}.  The caller chooses the grid shape (nx, nz, window) -- deposit.py:157-167 derives it from the
+ * statistics, so it is a guess (the previous step's) that the caller checks once the statistics have arrived; if it was
+ * right, d_fields / d_scalars are bitwise what dfcsr_get_df gives with the host-computed limits, and the GPU has not
+ * waited for the host in between. */
+int dfcsr_get_df_from_stats(const double* d_x, const double* d_z, const double* d_px, int64_t n, const double* d_stats,
+                            double xlim, double zlim, int32_t nx, int32_t nz, double* d_limits, int64_t* d_q,
+                            double* d_count, double* d_vxsum, uint64_t* d_count_max, int32_t window, const double* d_taps,
+                            const double* d_edge_lo, const double* d_edge_hi, double velocity_threshold, double* d_fields,
+                            double* d_scalars, void* d_workspace, void* stream);
+
 /* ---- A7 / K3 bilinear re-gridding into a history slot (deposit.py:296-309,328-332,379-390) -----
  * Samples the five fields of one raw density-function record (field stack on src axes) on the
  * history grid and writes one voxel slice.  Out-of-source points get 0, or the fill value for vx_x

@@ -94,6 +94,8 @@ SIGNATURES = {
     "dfcsr_make_df_workspace": (_L, [_I, _I]),
     "dfcsr_make_df": (C.c_int, [_P, _P, Axis, Axis, _I, _P, _P, _P, _D, _P, _P, _P, _P, _P]),
     "dfcsr_get_df": (C.c_int, [_P, _P, _P, _L, Axis, Axis, _D, _P, _P, _P, _P, _I, _P, _P, _P, _D, _P, _P, _P, _P]),
+    "dfcsr_get_df_from_stats": (C.c_int, [_P, _P, _P, _L, _P, _D, _D, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _D, _P, _P,
+                                          _P, _P]),
     "dfcsr_history_regrid": (C.c_int, [_P, Axis, Axis, Axis, Axis, _D, _P, _I, _P, _P, _P]),
     "dfcsr_history_row_support": (C.c_int, [_P, _I, _I, _I, _P, _P]),
     "dfcsr_history_pack": (C.c_int, [_P, _I, _I, _I, _P, _P]),

@@ -259,6 +259,7 @@ class CSR2D:
                 else:
                     b.track(self.get_bmadx_element(ele=ele, DL=DL), DL)
                 if debug or self.CSR_params.compute_CSR:                   # CSR.py:297-307
+                    self.DF_tracker.prefetch_DF(b)         # deposit + density functions enqueued behind the statistics pass
                     self.DF_tracker.get_DF(x=b.x, z=b.z, px=b.px, t=b.position, stats=b.stats)
                     self.DF_tracker.append_DF()
                     self.DF_tracker.append_interpolant(formation_length=self.formation_length,

@@ -11,6 +11,11 @@ void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* where);
 void count_launch(int n);   // kernels launched by this library (dfcsr_launch_count)
 
+// deposit.cu: both stages of the fixed-point deposit of one GPU, limits and max|px| taken from device memory
+int deposit_one_gpu_from_device(const double* d_x, const double* d_z, const double* d_px, long long n, int nx, int nz,
+                                const double* d_lim, const unsigned long long* d_wslot, long long* d_q, double* d_count,
+                                double* d_vxsum, unsigned long long* d_count_max, cudaStream_t st);
+
 #define DFCSR_CUDA_OK(expr)                                             \
     do {                                                                \
         cudaError_t _e = (expr);                                        \

@@ -214,6 +214,12 @@ struct VxScale {
     double tile, glob;           // 2^(f_tile - e), 2^(f_glob - e) with max|px| < 2^e; 0 if px is all zero or not finite
 };
 
+// device twin of absmax_bits(): a statistic that is negative, infinite or NaN means "not finite" (vxsum becomes NaN)
+__device__ __forceinline__ unsigned long long finite_or_nan_bits(unsigned long long bits) {
+    const double v = __longlong_as_double((long long)bits);
+    return (v >= 0.0 && v < CUDART_INF) ? bits : 0x7ff8000000000000ULL;
+}
+
 __device__ __forceinline__ VxScale vx_scale(unsigned long long wbits, FixedScales fs) {
     const double wmax = __longlong_as_double((long long)wbits);
     VxScale s;
@@ -271,14 +277,20 @@ __global__ void __launch_bounds__(kTile ? kTileThreads : 256, kTile ? 1 : 4)
 cic_fixed_kernel(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ px,
                  long long n, DepGrid g, Tile t, FixedScales fs, const unsigned long long* __restrict__ wslot,
                  unsigned long long wbits_value, unsigned long long* __restrict__ count,
-                 unsigned long long* __restrict__ vxsum) {
+                 unsigned long long* __restrict__ vxsum, const double* __restrict__ lim) {
     extern __shared__ unsigned ftile[];
+    if (lim) {      // grid limits {x_lo, x_hi, z_lo, z_hi} from device memory (dfcsr_get_df_from_stats): make_grid on the device
+        g.x_start = lim[0];
+        g.z_start = lim[2];
+        g.inv_dx = __ddiv_rn(1.0, __ddiv_rn(__dsub_rn(lim[1], lim[0]), (double)g.nx));
+        g.inv_dz = __ddiv_rn(1.0, __ddiv_rn(__dsub_rn(lim[3], lim[2]), (double)g.nz));
+    }
     const int cells = kTile ? t.ni * t.nj : 0;
     if (kTile) {
         for (int c = threadIdx.x; c < 4 * cells; c += blockDim.x) ftile[c] = 0u;
         __syncthreads();
     }
-    const VxScale vs = vx_scale(wslot ? *wslot : wbits_value, fs);
+    const VxScale vs = vx_scale(wslot ? (lim ? finite_or_nan_bits(*wslot) : *wslot) : wbits_value, fs);
     const double sc_t = scalbn(1.0, fs.f_tile), sc_g = scalbn(1.0, fs.f_glob);
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -359,7 +371,9 @@ struct PeerQ {
 
 __global__ void __launch_bounds__(256)
 cic_fixed_finish_peers(long long cells, FixedScales fs, unsigned long long wbits, PeerQ peers,
-                       double* __restrict__ count, double* __restrict__ vxsum, unsigned long long* __restrict__ count_max) {
+                       double* __restrict__ count, double* __restrict__ vxsum, unsigned long long* __restrict__ count_max,
+                       const unsigned long long* __restrict__ wslot) {
+    if (wslot) wbits = finite_or_nan_bits(*wslot);      // max|px| from device memory (bit pattern of the statistic)
     const VxScale vs = vx_scale(wbits, fs);
     const double inv_c = scalbn(1.0, -fs.f_glob);
     const double wmax = __longlong_as_double((long long)wbits);
@@ -484,7 +498,8 @@ static FixedScales fixed_scales(long long n_total) {
 // fixed-point deposit of n particles into the int64 grids c64 / v64 (not zeroed here)
 static int deposit_fixed_accumulate(const double* d_x, const double* d_z, const double* d_px, long long n, long long n_total,
                                     const DepGrid& g, const unsigned long long* d_wslot, unsigned long long wbits,
-                                    unsigned long long* c64, unsigned long long* v64, bool tiled, cudaStream_t st) {
+                                    unsigned long long* c64, unsigned long long* v64, bool tiled, cudaStream_t st,
+                                    const double* d_lim = nullptr) {
     const FixedScales fs = fixed_scales(n_total);
     if (tiled) {
         Tile t = make_tile(g.nx, g.nz);
@@ -492,12 +507,12 @@ static int deposit_fixed_accumulate(const double* d_x, const double* d_z, const 
         long long want = (n + kParticlesPerCta - 1) / kParticlesPerCta;
         unsigned blocks = (unsigned)(want < 148 ? (want < 1 ? 1 : want) : 148);
         DFCSR_CUDA_OK(cudaFuncSetAttribute(cic_fixed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cic_fixed_kernel<true><<<blocks, kTileThreads, smem, st>>>(d_x, d_z, d_px, n, g, t, fs, d_wslot, wbits, c64, v64);
+        cic_fixed_kernel<true><<<blocks, kTileThreads, smem, st>>>(d_x, d_z, d_px, n, g, t, fs, d_wslot, wbits, c64, v64, d_lim);
     } else {
         Tile t = {0, 0, 0, 0};
         long long want = (n + 255) / 256;
         unsigned blocks = (unsigned)(want < 148LL * 4 ? want : 148LL * 4);
-        cic_fixed_kernel<false><<<blocks, 256, 0, st>>>(d_x, d_z, d_px, n, g, t, fs, d_wslot, wbits, c64, v64);
+        cic_fixed_kernel<false><<<blocks, 256, 0, st>>>(d_x, d_z, d_px, n, g, t, fs, d_wslot, wbits, c64, v64, d_lim);
     }
     count_launch(1);
     DFCSR_CUDA_OK(cudaGetLastError());
@@ -616,11 +631,40 @@ extern "C" int dfcsr_deposit_cic_finish(const uint64_t* h_peer_q, int32_t n_peer
     if (d_count_max) DFCSR_CUDA_OK(cudaMemsetAsync(d_count_max, 0, sizeof(uint64_t), as_stream(stream)));
     cic_fixed_finish_peers<<<blocks, 256, 0, as_stream(stream)>>>(cells, fixed_scales(n_total), absmax_bits(absmax_px), pq,
                                                                   d_count, d_vxsum,
-                                                                  reinterpret_cast<unsigned long long*>(d_count_max));
+                                                                  reinterpret_cast<unsigned long long*>(d_count_max), nullptr);
     count_launch(1);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;
 }
+
+// Library-internal (common.cuh): the two stages of the fixed-point deposit of ONE GPU with the grid limits and max|px| read
+// from device memory -- d_lim = {x_lo, x_hi, z_lo, z_hi}, d_wslot = the max|px| statistic -- so that they can be enqueued
+// before the host has seen the statistics (dfcsr_get_df_from_stats).
+namespace dfcsr {
+int deposit_one_gpu_from_device(const double* d_x, const double* d_z, const double* d_px, long long n, int nx, int nz,
+                                const double* d_lim, const unsigned long long* d_wslot, long long* d_q, double* d_count,
+                                double* d_vxsum, unsigned long long* d_count_max, cudaStream_t st) {
+    const size_t cells = (size_t)nx * nz;
+    DFCSR_CUDA_OK(cudaMemsetAsync(d_q, 0, 2 * cells * sizeof(long long), st));
+    DepGrid g = make_grid(nx, 0.0, 1.0, nz, 0.0, 1.0);          // dimensions only: the kernel takes the limits from d_lim
+    unsigned long long* q = reinterpret_cast<unsigned long long*>(d_q);
+    if (n > 0) {
+        int rc = deposit_fixed_accumulate(d_x, d_z, d_px, n, n, g, d_wslot, 0ull, q, q + cells, n >= 65536, st, d_lim);
+        if (rc) return rc;
+    }
+    PeerQ pq;
+    pq.n = 1;
+    for (int p = 0; p < DFCSR_MAX_PEERS; ++p) pq.q[p] = p == 0 ? d_q : nullptr;
+    long long want = ((long long)cells + 255) / 256;
+    unsigned blocks = (unsigned)(want < 148LL * 4 ? want : 148LL * 4);
+    DFCSR_CUDA_OK(cudaMemsetAsync(d_count_max, 0, sizeof(unsigned long long), st));
+    cic_fixed_finish_peers<<<blocks, 256, 0, st>>>((long long)cells, fixed_scales(n), 0ull, pq, d_count, d_vxsum, d_count_max,
+                                                   d_wslot);
+    count_launch(1);
+    DFCSR_CUDA_OK(cudaGetLastError());
+    return DFCSR_OK;
+}
+}  // namespace dfcsr
 
 extern "C" int dfcsr_deposit_ngp(const double* d_x, const double* d_z, int64_t n, int32_t nx, double x_start,
                                  double x_end, int32_t nz, double z_start, double z_end, int64_t* d_count,

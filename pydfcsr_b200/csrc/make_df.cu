@@ -64,7 +64,30 @@ struct DfParams {
     double* t0;                            // raw smoothed density plane
     double* t1;                            // raw smoothed velocity plane
     int tiles_x, tiles_z;
+    const double* lim;                     // {x_lo, x_hi, z_lo, z_hi} in device memory, or nullptr: the axes above are final
 };
+
+// dfcsr_get_df_from_stats: the axis end points arrive in device memory (the launch was enqueued before the host saw the
+// statistics); numpy.linspace's step is rebuilt from them exactly as make_axis does on the host
+__device__ __forceinline__ void axes_from_device(DfParams& P) {
+    if (P.lim) {
+        P.ax = make_axis(P.lim[0], P.lim[1], P.ax.n);
+        P.az = make_axis(P.lim[2], P.lim[3], P.az.n);
+    }
+}
+
+// grid limits of DF_tracker.get_DF from the statistics vector (deposit.py:160-171: mean -+ lim * sigma), with the
+// roundings of the Python expression `mean - lim * sigma` (one multiplication, one addition, no contraction)
+__global__ void df_limits_kernel(const double* __restrict__ stats, double xlim, double zlim, double* __restrict__ lim) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const double mx = stats[DFCSR_S_MEAN_X], mz = stats[DFCSR_S_MEAN_Z];
+        const double hx = __dmul_rn(xlim, stats[DFCSR_S_SIGMA_X]), hz = __dmul_rn(zlim, stats[DFCSR_S_SIGMA_Z]);
+        lim[0] = __dsub_rn(mx, hx);
+        lim[1] = __dadd_rn(mx, hx);
+        lim[2] = __dsub_rn(mz, hz);
+        lim[3] = __dadd_rn(mz, hz);
+    }
+}
 
 // Savitzky-Golay along one axis for element i of a line of n samples; `at(k)` fetches sample k of the line.
 // kW > 0: compile-time window (fully unrolled taps); kW = 0: runtime window.  Same operations in the same order either way.
@@ -277,6 +300,7 @@ count_max_kernel(const double* __restrict__ count, int cells, unsigned long long
 __global__ void __launch_bounds__(kDfThreads)
 make_df_phase_a(DfParams P) {
     extern __shared__ double smem[];
+    axes_from_device(P);
     const TileGeom g = tile_geom(P);
     const int nz = P.az.n;
     const int half = P.window >> 1;
@@ -332,6 +356,7 @@ make_df_phase_a(DfParams P) {
 __global__ void __launch_bounds__(kDfThreads)
 make_df_phase_b(DfParams P) {
     extern __shared__ double smem[];
+    axes_from_device(P);
     const TileGeom g = tile_geom(P);
     const int nx = P.ax.n, nz = P.az.n;
     const int cells = nx * nz;
@@ -445,10 +470,10 @@ extern "C" int64_t dfcsr_make_df_workspace(int32_t nx, int32_t nz) {
            (int64_t)2 * nx * nz * (int64_t)sizeof(double);
 }
 
-extern "C" int dfcsr_make_df(const double* d_count, const double* d_vxsum, dfcsr_axis x_axis, dfcsr_axis z_axis,
-                             int32_t window, const double* d_taps, const double* d_edge_lo, const double* d_edge_hi,
-                             double velocity_threshold, const uint64_t* d_count_max, double* d_fields, double* d_scalars,
-                             void* d_workspace, void* stream) {
+static int make_df_impl(const double* d_count, const double* d_vxsum, dfcsr_axis x_axis, dfcsr_axis z_axis,
+                        int32_t window, const double* d_taps, const double* d_edge_lo, const double* d_edge_hi,
+                        double velocity_threshold, const uint64_t* d_count_max, double* d_fields, double* d_scalars,
+                        void* d_workspace, void* stream, const double* d_lim) {
     DFCSR_REQUIRE(d_count && d_vxsum && d_fields && d_scalars && d_workspace, "null device pointer");
     DFCSR_REQUIRE(d_taps && (window < 3 || (d_edge_lo && d_edge_hi)), "null operator pointer");
     DFCSR_REQUIRE(window >= 1 && (window & 1), "window must be odd and positive");
@@ -481,6 +506,7 @@ extern "C" int dfcsr_make_df(const double* d_count, const double* d_vxsum, dfcsr
     P.t1 = P.t0 + cells;
     P.tiles_x = (x_axis.n + kTile - 1) / kTile;
     P.tiles_z = (z_axis.n + kTile - 1) / kTile;
+    P.lim = d_lim;
     DFCSR_CUDA_OK(cudaMemsetAsync(P.hdr, 0, sizeof(DfHeader), st));      // tickets and the max slot
     int launches = 3;
     if (d_count_max) {
@@ -517,6 +543,41 @@ extern "C" int dfcsr_make_df(const double* d_count, const double* d_vxsum, dfcsr
     count_launch(launches);
     DFCSR_CUDA_OK(cudaGetLastError());
     return DFCSR_OK;
+}
+
+extern "C" int dfcsr_make_df(const double* d_count, const double* d_vxsum, dfcsr_axis x_axis, dfcsr_axis z_axis,
+                             int32_t window, const double* d_taps, const double* d_edge_lo, const double* d_edge_hi,
+                             double velocity_threshold, const uint64_t* d_count_max, double* d_fields, double* d_scalars,
+                             void* d_workspace, void* stream) {
+    return make_df_impl(d_count, d_vxsum, x_axis, z_axis, window, d_taps, d_edge_lo, d_edge_hi, velocity_threshold,
+                        d_count_max, d_fields, d_scalars, d_workspace, stream, nullptr);
+}
+
+// DF_tracker.get_DF enqueued BEFORE the host has the statistics (include/dfcsr_b200.h): limits kernel, both deposit
+// stages and the three density-function kernels, all reading the grid limits and max|px| from device memory
+extern "C" int dfcsr_get_df_from_stats(const double* d_x, const double* d_z, const double* d_px, int64_t n,
+                                       const double* d_stats, double xlim, double zlim, int32_t nx, int32_t nz,
+                                       double* d_limits, int64_t* d_q, double* d_count, double* d_vxsum,
+                                       uint64_t* d_count_max, int32_t window, const double* d_taps,
+                                       const double* d_edge_lo, const double* d_edge_hi, double velocity_threshold,
+                                       double* d_fields, double* d_scalars, void* d_workspace, void* stream) {
+    DFCSR_REQUIRE(d_stats && d_limits && d_q && d_count && d_vxsum && d_count_max, "null scratch / output pointer");
+    DFCSR_REQUIRE(n >= 1 && d_x && d_z && d_px, "the particle arrays (with px) are required");
+    DFCSR_REQUIRE(nx >= 1 && nz >= 1 && (long long)nx * nz < (1LL << 30), "bad grid");
+    cudaStream_t st = as_stream(stream);
+    df_limits_kernel<<<1, 32, 0, st>>>(d_stats, xlim, zlim, d_limits);
+    count_launch(1);
+    DFCSR_CUDA_OK(cudaGetLastError());
+    int rc = deposit_one_gpu_from_device(d_x, d_z, d_px, n, nx, nz, d_limits,
+                                         reinterpret_cast<const unsigned long long*>(d_stats + DFCSR_S_ABSMAX_PX),
+                                         reinterpret_cast<long long*>(d_q), d_count, d_vxsum,
+                                         reinterpret_cast<unsigned long long*>(d_count_max), st);
+    if (rc) return rc;
+    dfcsr_axis xa, za;                     // dimensions only: the kernels take the end points from d_limits
+    xa.start = 0.0; xa.stop = 1.0; xa.n = nx; xa._pad = 0;
+    za.start = 0.0; za.stop = 1.0; za.n = nz; za._pad = 0;
+    return make_df_impl(d_count, d_vxsum, xa, za, window, d_taps, d_edge_lo, d_edge_hi, velocity_threshold, d_count_max,
+                        d_fields, d_scalars, d_workspace, stream, d_limits);
 }
 
 // DF_tracker.get_DF on one GPU in one call (include/dfcsr_b200.h): the three stages back to back on one stream

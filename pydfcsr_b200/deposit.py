@@ -17,6 +17,7 @@ from collections import deque
 from dataclasses import dataclass
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -81,6 +82,11 @@ class DF_tracker:
         self._deposit_scratch = None
         self._q_scratch = None
         self._count_max = None
+        self._spec_shape = None        # (xb, zb, window) of the last get_DF: the guess of the next prefetch_DF
+        self._spec = None              # what prefetch_DF has enqueued, until get_DF adopts or discards it
+        self._limits = None
+        self.prefetch_hits = 0         # get_DF calls served by a prefetch (diagnostics)
+        self.prefetch = os.environ.get("DFCSR_PREFETCH_DF", "1") != "0"
         self.shards = shards           # distributed.ParticleShards when x, z, px are this rank's shard of the bunch
 
     def configure_params(self, xbins=100, zbins=100, xlim=5, zlim=5, filter_order=0, filter_window=0,
@@ -102,6 +108,35 @@ class DF_tracker:
             return a.to(self.device, torch.float64).contiguous()
         return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device, non_blocking=True)
 
+    def prefetch_DF(self, beam):
+        """Optional, between `Beam.update_status()` and `get_DF`: enqueue the deposit and the density functions of the
+        beam's current state NOW, behind the statistics pass that is still in flight, with the grid limits and max|px|
+        read from the device (dfcsr_get_df_from_stats).  The grid shape (deposit.py:157-167 derives it from the statistics)
+        is a guess: the previous step's.  `get_DF` checks the guess when the statistics have arrived and adopts the
+        result -- same bits as computing it then -- or discards it.  Saves the GPU the wait for the host round trip
+        statistics -> Python -> five launches at the start of every lattice step.  No-op when there is nothing to go on."""
+        self._spec = None
+        pending = getattr(beam, "_pending_stats", None)
+        if (not self.prefetch or self._spec_shape is None or self.shards is not None or self.deposit_mode != 0 or pending is None
+                or pending.device_stats is None or pending._value is not None or beam.px is None):
+            return
+        xb, zb, window = self._spec_shape
+        x, z, px = beam.x, beam.z, beam.px
+        if not (x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and z.is_contiguous() and px.is_contiguous()):
+            return
+        if self._deposit_scratch is None or self._deposit_scratch.shape[1:] != (xb, zb):
+            self._deposit_scratch = torch.empty((2, xb, zb), dtype=torch.float64, device=self.device)
+        if self._count_max is None:
+            self._count_max = torch.zeros(1, dtype=torch.int64, device=self.device)
+        if self._q_scratch is None or self._q_scratch.numel() < 2 * xb * zb:
+            self._q_scratch = torch.empty(2 * xb * zb, dtype=torch.int64, device=self.device)
+        if self._limits is None:
+            self._limits = torch.empty(4, dtype=torch.float64, device=self.device)
+        fields, scalars = ops.get_df_from_stats(x, z, px, pending.device_stats, self.xlim, self.zlim, xb, zb, window,
+                                                self.filter_order, self.velocity_threhold, self._q_scratch,
+                                                self._deposit_scratch, self._count_max, self._limits)
+        self._spec = (pending, x.data_ptr(), z.data_ptr(), px.data_ptr(), (xb, zb, window), fields, scalars)
+
     def get_DF(self, x, z, px, t, stats=None):
         """x, z, px: CUDA tensors (host arrays are uploaded).  `stats` may carry the 16 beam scalars
         already computed by Beam.update_status so that the reduction kernels run once per step."""
@@ -118,6 +153,17 @@ class DF_tracker:
             xb, zb, window = 100, 100, 5                               # deposit.py:164-167
         x_lo, x_hi = xmean - self.xlim * sigma_x, xmean + self.xlim * sigma_x
         z_lo, z_hi = zmean - self.zlim * sigma_z, zmean + self.zlim * sigma_z
+        self._spec_shape = (xb, zb, window)
+        spec, self._spec = self._spec, None
+        if (spec is not None and spec[0]._value is stats and spec[1:4] == (x.data_ptr(), z.data_ptr(), px.data_ptr())
+                and spec[4] == (xb, zb, window)):
+            # prefetch_DF has already enqueued exactly this computation (limits taken from the device statistics with the
+            # roundings of the two lines above): adopt it
+            x_axis, z_axis = Axis.make(x_lo, x_hi, xb), Axis.make(z_lo, z_hi, zb)
+            self._current = _Record(spec[5], spec[6], x_axis, z_axis, t, sigma_x, sigma_z, xmean, zmean)
+            self.t = t
+            self.prefetch_hits += 1
+            return
         if self._deposit_scratch is None or self._deposit_scratch.shape[1:] != (xb, zb):
             self._deposit_scratch = torch.empty((2, xb, zb), dtype=torch.float64, device=self.device)
         absmax = float(stats[_lib.S_ABSMAX_PX]) if len(stats) > _lib.S_ABSMAX_PX else -1.0

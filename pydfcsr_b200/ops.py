@@ -66,8 +66,9 @@ class PendingStats:
     The pinned buffer belongs to this object until it has been read (or the object dies); only then does it go back
     to the free list, so a result that is read late can never be overwritten by a later pass."""
 
-    def __init__(self, host_buf, event, free_list):
+    def __init__(self, host_buf, event, free_list, device_stats=None):
         self._buf, self._event, self._value, self._free = host_buf, event, None, free_list
+        self.device_stats = device_stats      # the 16 doubles on the device (input of get_df_from_stats)
 
     def _release(self):
         if self._buf is not None:
@@ -133,7 +134,7 @@ def beam_stats_async(x: torch.Tensor, z: torch.Tensor, pz: torch.Tensor | None =
         host.copy_(d_stats, non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()
-    return PendingStats(host, ev, free)
+    return PendingStats(host, ev, free, d_stats)
 
 
 def beam_stats(x: torch.Tensor, z: torch.Tensor, pz: torch.Tensor | None = None, px: torch.Tensor | None = None,
@@ -331,6 +332,36 @@ def get_df(x, z, px, x_axis: Axis, z_axis: Axis, absmax_px, window: int, order: 
     return fields, scalars
 
 
+def get_df_from_stats(x, z, px, d_stats: torch.Tensor, xlim: float, zlim: float, nx: int, nz: int, window: int, order: int,
+                      velocity_threshold: float, q_scratch: torch.Tensor, deposit_out: torch.Tensor, count_max: torch.Tensor,
+                      limits: torch.Tensor):
+    """get_df enqueued BEFORE the host has the statistics (dfcsr_get_df_from_stats): grid limits and max|px| come from
+    `d_stats`, the device vector of the statistics pass that is still in flight on this stream; `limits` (4 doubles on the
+    device) receives the limits.  The grid shape is the caller's guess.  Returns (fields, scalars)."""
+    dev = x.device
+    need = _df_need.get((nx, nz))
+    if need is None:
+        need = _df_need[(nx, nz)] = lib.dfcsr_make_df_workspace(nx, nz)
+    ws = _df_ws.get(dev)
+    if ws is None or ws.numel() < need:
+        ws = _df_ws[dev] = torch.empty(need, dtype=torch.uint8, device=dev)
+    key = (window, order, dev)
+    if key not in _sg_dev:
+        _sg_dev[key] = tuple(torch.from_numpy(a.reshape(-1).copy()).to(dev) if a.size else None
+                             for a in savgol_operators(window, order))
+    taps, lo, hi = _sg_dev[key]
+    if q_scratch.dtype != torch.int64 or q_scratch.numel() < 2 * nx * nz or tuple(deposit_out.shape) != (2, nx, nz):
+        raise _lib.DfcsrError("get_df_from_stats: q_scratch must hold 2*nx*nz int64 and deposit_out must be (2, nx, nz)")
+    fields = torch.empty((5, nx, nz), dtype=F64, device=dev)
+    scalars = torch.empty(_lib.DF_SCALARS, dtype=F64, device=dev)
+    check(lib.dfcsr_get_df_from_stats(_ptr(_f64(x, "x")), _ptr(_f64(z, "z")), _ptr(_f64(px, "px")), x.numel(), _ptr(d_stats),
+                                      float(xlim), float(zlim), nx, nz, _ptr(limits), _ptr(q_scratch), _ptr(deposit_out[0]),
+                                      _ptr(deposit_out[1]), _ptr(count_max), window, _ptr(taps), _ptr(lo), _ptr(hi),
+                                      float(velocity_threshold), _ptr(fields), _ptr(scalars), _ptr(ws), _stream()),
+          "dfcsr_get_df_from_stats")
+    return fields, scalars
+
+
 # ---------------------------------------------------------------------------------------------
 # 2-D Savitzky-Golay operator (SGolay_filter.py:3-81)
 # ---------------------------------------------------------------------------------------------
@@ -494,13 +525,18 @@ class DeviceHistory:
     support: torch.Tensor | None = None   # (cap, X, 2) int32 row hulls of the non-zero density voxels, or None
 
     def view(self) -> _lib.History:
+        v = self.__dict__.get("_view")            # one struct per published history (a wake step asks for it 2-3 times)
+        if v is not None:
+            return v
         cap, X, Z, elems = self.ring.shape
         if self.support is not None and (self.support.dtype != torch.int32 or tuple(self.support.shape) != (cap, X, 2)
                                          or not self.support.is_contiguous()):
             raise _lib.DfcsrError("row support must be a contiguous (cap, X, 2) int32 tensor")
-        return _lib.History(self.ring.data_ptr(), X * Z * elems, cap, self.head, self.T, X, Z, voxel_format(self.ring),
-                            self.min_t, self.min_x, self.min_z, self.delta_t, self.delta_x, self.delta_z,
-                            None if self.support is None else self.support.data_ptr())
+        v = self.__dict__["_view"] = _lib.History(
+            self.ring.data_ptr(), X * Z * elems, cap, self.head, self.T, X, Z, voxel_format(self.ring),
+            self.min_t, self.min_x, self.min_z, self.delta_t, self.delta_x, self.delta_z,
+            None if self.support is None else self.support.data_ptr())
+        return v
 
     @classmethod
     def from_stacks(cls, stacks, min_t, min_x, min_z, delta_t, delta_x, delta_z, device, cap=None, head=0,

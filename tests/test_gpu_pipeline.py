@@ -269,3 +269,48 @@ def test_yaml_driven_run_matches_reference_schema(tmp_path, monkeypatch):
     assert bool(torch.isfinite(csr.dE_dct).all()) and float(csr.dE_dct.abs().max()) > 0
     with pytest.raises(AssertionError):
         CSR2D(input_file={"input_beam": {"style": "synthetic", "n_particle": 10}, "input_lattice": {}, "bogus": 1})
+
+
+def test_prefetched_density_functions_are_bitwise_the_synchronous_ones():
+    """DF_tracker.prefetch_DF enqueues deposit + density functions behind the statistics pass with the grid limits and
+    max|px| read from the device (dfcsr_get_df_from_stats); get_DF adopts the result when its guess of the grid shape was
+    right.  Fields, scalars and the record's axes must be the bits of the synchronous path (deposit.py:145-245), for both
+    grid branches (deposit.py:157-167), and a wrong guess must fall back to the synchronous path."""
+    import torch
+    from pydfcsr_b200 import CSR2D, synth
+
+    def make(prefetch):
+        inp = {"input_beam": {"style": "synthetic", "n_particle": 200_000, "seed": 11},
+               "input_lattice": {"lattice_config": synth.chicane_lattice_config()},
+               "particle_deposition": dict(xbins=120, zbins=90, xlim=5, zlim=5, filter_order=1, filter_window=9,
+                                           velocity_threhold=1000, upper_limit=1000),
+               "CSR_integration": dict(n_formation_length=1, zbins=40, xbins=40),
+               "CSR_computation": dict(compute_CSR=1, apply_CSR=1, transverse_on=1, xbins=6, zbins=9, xlim=3, zlim=3,
+                                       write_beam=None, write_wakes=False, workdir="/tmp/dfcsr_test")}
+        csr = CSR2D(inp, parallel=False, device="cuda:0", verbose=False)
+        csr.DF_tracker.prefetch = prefetch
+        return csr
+
+    a, b = make(True), make(False)
+    a.run(stop_time=2.6)
+    b.run(stop_time=2.6)
+    ta, tb = a.DF_tracker, b.DF_tracker
+    assert ta.prefetch_hits > 10 and tb.prefetch_hits == 0
+    ra, rb = ta._current, tb._current
+    assert torch.equal(ra.fields, rb.fields) and torch.equal(ra.scalars, rb.scalars)
+    assert (ra.x_axis.start, ra.x_axis.stop, ra.z_axis.start, ra.z_axis.stop) == (rb.x_axis.start, rb.x_axis.stop,
+                                                                                 rb.z_axis.start, rb.z_axis.stop)
+    assert torch.equal(a.dE_dct, b.dE_dct) and torch.equal(a.x_kick, b.x_kick)
+    for u, v in zip(a.beam.coords, b.beam.coords):
+        assert torch.equal(u, v)
+    # the limits the device computed are the host's (same roundings)
+    lim = ta._limits.cpu().numpy()
+    assert (lim[0], lim[1], lim[2], lim[3]) == (ra.x_axis.start, ra.x_axis.stop, ra.z_axis.start, ra.z_axis.stop)
+    # a wrong guess of the grid shape is discarded
+    hits = ta.prefetch_hits
+    ta._spec_shape = (64, 64, 5)
+    a.beam.update_status()
+    ta.prefetch_DF(a.beam)
+    ta.get_DF(x=a.beam.x, z=a.beam.z, px=a.beam.px, t=a.beam.position, stats=a.beam.stats)
+    tb.get_DF(x=b.beam.x, z=b.beam.z, px=b.beam.px, t=b.beam.position, stats=b.beam.stats)
+    assert ta.prefetch_hits == hits and torch.equal(ta._current.fields, tb._current.fields)

@@ -35,7 +35,7 @@ def stage(name, fn):
 
 def one_step():
     stage("restore", lambda: (beam.coords[1].copy_(pristine[1]), beam.coords[5].copy_(pristine[5])))
-    stage("stats#1 (sync)", beam.update_status)
+    stage("stats#1 (enqueue) + prefetch", lambda: (beam.update_status(), trk.prefetch_DF(beam)))
     stage("get_DF (K1+K2)", lambda: trk.get_DF(x=beam.x, z=beam.z, px=beam.px, t=beam.position, stats=beam.stats))
     stage("append+regrid (K3)", lambda: (trk.append_DF(), trk.append_interpolant(csr.formation_length, 1), trk.build_interpolant()))
     stage("mesh (host+H2D)", csr.get_CSR_mesh)
