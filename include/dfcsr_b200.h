@@ -255,6 +255,19 @@ int dfcsr_get_df_from_stats(const double* d_x, const double* d_z, const double* 
                             const double* d_edge_lo, const double* d_edge_hi, double velocity_threshold, double* d_fields,
                             double* d_scalars, void* d_workspace, void* stream);
 
+/* The stages of dfcsr_get_df_from_stats one by one, for particles sharded over ranks (a cross-rank barrier separates the
+ * two deposit stages, as with dfcsr_deposit_cic_q / _finish): dfcsr_df_limits writes {x_lo, x_hi, z_lo, z_hi} from the
+ * device statistics; the _dev forms take the limits from d_limits and max|px| from d_stats instead of host scalars. */
+int dfcsr_df_limits(const double* d_stats, double xlim, double zlim, double* d_limits, void* stream);
+int dfcsr_deposit_cic_q_dev(const double* d_x, const double* d_z, const double* d_px, int64_t n_local, int64_t n_total,
+                            int32_t nx, int32_t nz, const double* d_limits, const double* d_stats, int64_t* d_q, void* stream);
+int dfcsr_deposit_cic_finish_dev(const uint64_t* h_peer_q, int32_t n_peers, int32_t nx, int32_t nz, int64_t n_total,
+                                 const double* d_stats, double* d_count, double* d_vxsum, uint64_t* d_count_max, void* stream);
+int dfcsr_make_df_dev(const double* d_count, const double* d_vxsum, int32_t nx, int32_t nz, const double* d_limits,
+                      int32_t window, const double* d_taps, const double* d_edge_lo, const double* d_edge_hi,
+                      double velocity_threshold, const uint64_t* d_count_max, double* d_fields, double* d_scalars,
+                      void* d_workspace, void* stream);
+
 /* ---- A7 / K3 bilinear re-gridding into a history slot (deposit.py:296-309,328-332,379-390) -----
  * Samples the five fields of one raw density-function record (field stack on src axes) on the
  * history grid and writes one voxel slice.  Out-of-source points get 0, or the fill value for vx_x

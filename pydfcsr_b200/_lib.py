@@ -96,6 +96,10 @@ SIGNATURES = {
     "dfcsr_get_df": (C.c_int, [_P, _P, _P, _L, Axis, Axis, _D, _P, _P, _P, _P, _I, _P, _P, _P, _D, _P, _P, _P, _P]),
     "dfcsr_get_df_from_stats": (C.c_int, [_P, _P, _P, _L, _P, _D, _D, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _D, _P, _P,
                                           _P, _P]),
+    "dfcsr_df_limits": (C.c_int, [_P, _D, _D, _P, _P]),
+    "dfcsr_deposit_cic_q_dev": (C.c_int, [_P, _P, _P, _L, _L, _I, _I, _P, _P, _P, _P]),
+    "dfcsr_deposit_cic_finish_dev": (C.c_int, [C.POINTER(C.c_uint64), _I, _I, _I, _L, _P, _P, _P, _P, _P]),
+    "dfcsr_make_df_dev": (C.c_int, [_P, _P, _I, _I, _P, _I, _P, _P, _P, _D, _P, _P, _P, _P, _P]),
     "dfcsr_history_regrid": (C.c_int, [_P, Axis, Axis, Axis, Axis, _D, _P, _I, _P, _P, _P]),
     "dfcsr_history_row_support": (C.c_int, [_P, _I, _I, _I, _P, _P]),
     "dfcsr_history_pack": (C.c_int, [_P, _I, _I, _I, _P, _P]),

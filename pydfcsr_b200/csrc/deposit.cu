@@ -666,6 +666,48 @@ int deposit_one_gpu_from_device(const double* d_x, const double* d_z, const doub
 }
 }  // namespace dfcsr
 
+// The two stages of a particle-sharded deposit with the grid limits (d_limits = {x_lo, x_hi, z_lo, z_hi}) and max|px|
+// (the statistic in d_stats) read from device memory: for DF_tracker.prefetch_DF with particle shards.
+extern "C" int dfcsr_deposit_cic_q_dev(const double* d_x, const double* d_z, const double* d_px, int64_t n_local,
+                                       int64_t n_total, int32_t nx, int32_t nz, const double* d_limits,
+                                       const double* d_stats, int64_t* d_q, void* stream) {
+    DFCSR_REQUIRE(d_q && d_limits && d_stats && (n_local == 0 || (d_x && d_z && d_px)), "null pointer");
+    DFCSR_REQUIRE(nx >= 1 && nz >= 1 && n_local >= 0 && n_total >= n_local && n_total >= 1, "bad sizes");
+    DFCSR_REQUIRE((long long)nx * nz < (1LL << 30), "grid too large");
+    cudaStream_t st = as_stream(stream);
+    const size_t cells = (size_t)nx * nz;
+    DFCSR_CUDA_OK(cudaMemsetAsync(d_q, 0, 2 * cells * sizeof(int64_t), st));
+    if (n_local == 0) return DFCSR_OK;
+    DepGrid g = make_grid(nx, 0.0, 1.0, nz, 0.0, 1.0);          // dimensions only
+    unsigned long long* q = reinterpret_cast<unsigned long long*>(d_q);
+    return deposit_fixed_accumulate(d_x, d_z, d_px, n_local, n_total, g,
+                                    reinterpret_cast<const unsigned long long*>(d_stats + DFCSR_S_ABSMAX_PX), 0ull, q, q + cells,
+                                    n_local >= 65536, st, d_limits);
+}
+
+extern "C" int dfcsr_deposit_cic_finish_dev(const uint64_t* h_peer_q, int32_t n_peers, int32_t nx, int32_t nz,
+                                            int64_t n_total, const double* d_stats, double* d_count, double* d_vxsum,
+                                            uint64_t* d_count_max, void* stream) {
+    DFCSR_REQUIRE(h_peer_q && n_peers >= 1 && n_peers <= DFCSR_MAX_PEERS && d_count && d_vxsum && d_stats, "bad argument");
+    DFCSR_REQUIRE(nx >= 1 && nz >= 1 && n_total >= 1, "bad sizes");
+    PeerQ pq;
+    pq.n = n_peers;
+    for (int p = 0; p < DFCSR_MAX_PEERS; ++p) {
+        pq.q[p] = p < n_peers ? reinterpret_cast<const long long*>(static_cast<uintptr_t>(h_peer_q[p])) : nullptr;
+        DFCSR_REQUIRE(p >= n_peers || pq.q[p] != nullptr, "null peer grid");
+    }
+    const long long cells = (long long)nx * nz;
+    long long want = (cells + 255) / 256;
+    unsigned blocks = (unsigned)(want < 148LL * 4 ? want : 148LL * 4);
+    if (d_count_max) DFCSR_CUDA_OK(cudaMemsetAsync(d_count_max, 0, sizeof(uint64_t), as_stream(stream)));
+    cic_fixed_finish_peers<<<blocks, 256, 0, as_stream(stream)>>>(
+        cells, fixed_scales(n_total), 0ull, pq, d_count, d_vxsum, reinterpret_cast<unsigned long long*>(d_count_max),
+        reinterpret_cast<const unsigned long long*>(d_stats + DFCSR_S_ABSMAX_PX));
+    count_launch(1);
+    DFCSR_CUDA_OK(cudaGetLastError());
+    return DFCSR_OK;
+}
+
 extern "C" int dfcsr_deposit_ngp(const double* d_x, const double* d_z, int64_t n, int32_t nx, double x_start,
                                  double x_end, int32_t nz, double z_start, double z_end, int64_t* d_count,
                                  void* stream) {

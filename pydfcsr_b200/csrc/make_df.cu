@@ -580,6 +580,26 @@ extern "C" int dfcsr_get_df_from_stats(const double* d_x, const double* d_z, con
                         d_fields, d_scalars, d_workspace, stream, d_limits);
 }
 
+extern "C" int dfcsr_df_limits(const double* d_stats, double xlim, double zlim, double* d_limits, void* stream) {
+    DFCSR_REQUIRE(d_stats && d_limits, "null pointer");
+    df_limits_kernel<<<1, 32, 0, as_stream(stream)>>>(d_stats, xlim, zlim, d_limits);
+    count_launch(1);
+    DFCSR_CUDA_OK(cudaGetLastError());
+    return DFCSR_OK;
+}
+
+extern "C" int dfcsr_make_df_dev(const double* d_count, const double* d_vxsum, int32_t nx, int32_t nz, const double* d_limits,
+                                 int32_t window, const double* d_taps, const double* d_edge_lo, const double* d_edge_hi,
+                                 double velocity_threshold, const uint64_t* d_count_max, double* d_fields, double* d_scalars,
+                                 void* d_workspace, void* stream) {
+    DFCSR_REQUIRE(d_limits, "null limits pointer");
+    dfcsr_axis xa, za;                     // dimensions only: the kernels take the end points from d_limits
+    xa.start = 0.0; xa.stop = 1.0; xa.n = nx; xa._pad = 0;
+    za.start = 0.0; za.stop = 1.0; za.n = nz; za._pad = 0;
+    return make_df_impl(d_count, d_vxsum, xa, za, window, d_taps, d_edge_lo, d_edge_hi, velocity_threshold, d_count_max,
+                        d_fields, d_scalars, d_workspace, stream, d_limits);
+}
+
 // DF_tracker.get_DF on one GPU in one call (include/dfcsr_b200.h): the three stages back to back on one stream
 extern "C" int dfcsr_get_df(const double* d_x, const double* d_z, const double* d_px, int64_t n, dfcsr_axis x_axis,
                             dfcsr_axis z_axis, double absmax_px, int64_t* d_q, double* d_count, double* d_vxsum,

@@ -87,6 +87,7 @@ class DF_tracker:
         self._limits = None
         self.prefetch_hits = 0         # get_DF calls served by a prefetch (diagnostics)
         self.prefetch = os.environ.get("DFCSR_PREFETCH_DF", "1") != "0"
+        self.prefetch_shards = os.environ.get("DFCSR_PREFETCH_DF_SHARDS", "1") != "0"
         self.shards = shards           # distributed.ParticleShards when x, z, px are this rank's shard of the bunch
 
     def configure_params(self, xbins=100, zbins=100, xlim=5, zlim=5, filter_order=0, filter_window=0,
@@ -117,8 +118,10 @@ class DF_tracker:
         statistics -> Python -> five launches at the start of every lattice step.  No-op when there is nothing to go on."""
         self._spec = None
         pending = getattr(beam, "_pending_stats", None)
-        if (not self.prefetch or self._spec_shape is None or self.shards is not None or self.deposit_mode != 0 or pending is None
+        if (not self.prefetch or self._spec_shape is None or self.deposit_mode != 0 or pending is None
                 or pending.device_stats is None or pending._value is not None or beam.px is None):
+            return
+        if self.shards is not None and not self.prefetch_shards:
             return
         xb, zb, window = self._spec_shape
         x, z, px = beam.x, beam.z, beam.px
@@ -132,6 +135,14 @@ class DF_tracker:
             self._q_scratch = torch.empty(2 * xb * zb, dtype=torch.int64, device=self.device)
         if self._limits is None:
             self._limits = torch.empty(4, dtype=torch.float64, device=self.device)
+        if self.shards is not None:
+            # every rank holds the same statistics, hence the same guess, and takes the same decision in get_DF: the
+            # barriers of the sharded deposit stay matched across ranks whether the result is adopted or not
+            fields, scalars = ops.get_df_from_stats_sharded(x, z, px, pending.device_stats, self.xlim, self.zlim, xb, zb, window,
+                                                            self.filter_order, self.velocity_threhold, self.shards,
+                                                            self._deposit_scratch, self._count_max, self._limits)
+            self._spec = (pending, x.data_ptr(), z.data_ptr(), px.data_ptr(), (xb, zb, window), fields, scalars)
+            return
         fields, scalars = ops.get_df_from_stats(x, z, px, pending.device_stats, self.xlim, self.zlim, xb, zb, window,
                                                 self.filter_order, self.velocity_threhold, self._q_scratch,
                                                 self._deposit_scratch, self._count_max, self._limits)

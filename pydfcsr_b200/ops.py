@@ -362,6 +362,46 @@ def get_df_from_stats(x, z, px, d_stats: torch.Tensor, xlim: float, zlim: float,
     return fields, scalars
 
 
+def _df_scratch(nx, nz, window, order, dev):
+    """(workspace, taps, edge_lo, edge_hi) of make_df for this grid and filter on this device (cached)."""
+    need = _df_need.get((nx, nz))
+    if need is None:
+        need = _df_need[(nx, nz)] = lib.dfcsr_make_df_workspace(nx, nz)
+    ws = _df_ws.get(dev)
+    if ws is None or ws.numel() < need:
+        ws = _df_ws[dev] = torch.empty(need, dtype=torch.uint8, device=dev)
+    key = (window, order, dev)
+    if key not in _sg_dev:
+        _sg_dev[key] = tuple(torch.from_numpy(a.reshape(-1).copy()).to(dev) if a.size else None
+                             for a in savgol_operators(window, order))
+    return (ws,) + _sg_dev[key]
+
+
+def get_df_from_stats_sharded(x, z, px, d_stats: torch.Tensor, xlim: float, zlim: float, nx: int, nz: int, window: int,
+                              order: int, velocity_threshold: float, shards, deposit_out: torch.Tensor,
+                              count_max: torch.Tensor, limits: torch.Tensor):
+    """get_df_from_stats for a bunch sharded over ranks: limits kernel, this rank's fixed-point deposit, the exact integer
+    sum over the ranks (peer mappings + one device-side barrier, or an NCCL all-reduce) fused with the conversion, density
+    functions -- all with limits / max|px| from the device statistics, nothing waits for the host.  Collective."""
+    dev = x.device
+    ws, taps, lo, hi = _df_scratch(nx, nz, window, order, dev)
+    st = _stream()
+    check(lib.dfcsr_df_limits(_ptr(d_stats), float(xlim), float(zlim), _ptr(limits), st), "dfcsr_df_limits")
+    q, ptrs = shards.q_buffer(nx * nz)
+    check(lib.dfcsr_deposit_cic_q_dev(_ptr(_f64(x, "x")), _ptr(_f64(z, "z")), _ptr(_f64(px, "px")), x.numel(),
+                                      int(shards.n_total), nx, nz, _ptr(limits), _ptr(d_stats), _ptr(q), st),
+          "dfcsr_deposit_cic_q_dev")
+    shards.reduce_q(q)
+    check(lib.dfcsr_deposit_cic_finish_dev(ptrs, len(ptrs), nx, nz, int(shards.n_total), _ptr(d_stats), _ptr(deposit_out[0]),
+                                           _ptr(deposit_out[1]), _ptr(count_max), _stream()), "dfcsr_deposit_cic_finish_dev")
+    fields = torch.empty((5, nx, nz), dtype=F64, device=dev)
+    scalars = torch.empty(_lib.DF_SCALARS, dtype=F64, device=dev)
+    check(lib.dfcsr_make_df_dev(_ptr(deposit_out[0]), _ptr(deposit_out[1]), nx, nz, _ptr(limits), window, _ptr(taps), _ptr(lo),
+                                _ptr(hi), float(velocity_threshold), _ptr(count_max), _ptr(fields), _ptr(scalars), _ptr(ws),
+                                _stream()), "dfcsr_make_df_dev")
+    return fields, scalars
+
+
 # ---------------------------------------------------------------------------------------------
 # 2-D Savitzky-Golay operator (SGolay_filter.py:3-81)
 # ---------------------------------------------------------------------------------------------
